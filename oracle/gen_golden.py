@@ -1,0 +1,148 @@
+"""Generate tests/golden/* by executing the UNMODIFIED reference (/root/reference) on oracle/minisimpy.py.
+
+TEST INFRASTRUCTURE ONLY.  Run in the build container (needs /root/reference):
+    python -m oracle.gen_golden            # all scenarios
+    python -m oracle.gen_golden ss_cfg1    # one
+
+Each ``tests/golden/<name>.npz`` holds, for one replication of one scenario: the ordered record stream
+(ring u16, time f32, value f32), the four variate tapes (A,B,D f32; C f64), the SimPy step count, the patch
+set, and the JSON-encoded scenario (config/resources/products/policy/seed) so that tests can rebuild the
+exact inputs on a box that has no /root/reference.
+"""
+from __future__ import annotations
+
+import copy
+import json
+import sys
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent.parent
+sys.path.insert(0, str(ROOT))
+
+from manusim_b200 import scenarios as sc  # noqa: E402
+from oracle import run_reference as rr  # noqa: E402
+
+GOLDEN = ROOT / "tests" / "golden"
+
+
+def _example(name):
+    sim, res, prod, exp = rr.load_example(name)
+    return copy.deepcopy(sim), copy.deepcopy(res), copy.deepcopy(prod), exp
+
+
+def scenario_table():
+    """name -> dict(cfg, resources, products, policy, seed, patches)."""
+    out = {}
+    cfg, res, prod = sc.toy2()
+    out["toy2"] = dict(cfg=cfg, resources=res, products=prod, policy="base", seed=1, patches=[])
+    cfg, res, prod = sc.toy2(warmup=25, mode="instantly", run_until=150)
+    out["toy2_instantly"] = dict(cfg=cfg, resources=res, products=prod, policy="base", seed=1, patches=[])
+
+    sim, res, prod, _ = _example("simple_scheduler")
+    sim["memory_size"] = 100000
+    sim.pop("print_mode", None)
+    out["ss_cfg1"] = dict(cfg=sim, resources=res, products=prod, policy="simple_scheduler", seed=54907, patches=[])
+
+    sim2 = dict(sim, run_until=400)
+    dres, dprod = sc.make_deterministic(res, prod)
+    out["ss_det"] = dict(cfg=sim2, resources=dres, products=dprod, policy="simple_scheduler", seed=3, patches=[])
+
+    sim3 = dict(sim, run_until=400, warmup=30, delivery_mode="instantly")
+    out["ss_instantly"] = dict(cfg=sim3, resources=res, products=prod, policy="base", seed=280679, patches=[])
+
+    # lots: demand quantity uniform -> round(x, 0) in {2,3,4}; batch sums with count > 1
+    lot_prod = copy.deepcopy(prod)
+    for p in lot_prod.values():
+        p["demand"]["quantity"] = {"dist": "uniform", "params": [3, 0.5]}
+        p["demand"]["freq"] = {"dist": "expo", "params": [34]}
+        p["demand"]["duedate"] = {"dist": "normal", "params": [60, 25]}
+    sim4 = dict(sim, run_until=500, warmup=40)
+    out["ss_lots"] = dict(cfg=sim4, resources=res, products=lot_prod, policy="base", seed=91421, patches=[])
+
+    cfg, res20, prod20 = sc.jobshop20(run_until=1200, warmup=150, mode="asReady")
+    out["js20_asready"] = dict(cfg=cfg, resources=res20, products=prod20, policy="base", seed=20260101, patches=[])
+    cfg, res20, prod20 = sc.jobshop20(run_until=1200, warmup=150, mode="onDue")
+    out["js20_ondue"] = dict(cfg=cfg, resources=res20, products=prod20, policy="base", seed=20260102, patches=["P1"])
+    # frequent breakdowns so TTR/TBF logic is exercised inside a short run
+    cfg, res20b, prod20b = sc.jobshop20(run_until=1200, warmup=150, mode="asReady")
+    for i, r in enumerate(res20b.values()):
+        r["tbf"] = {"dist": "expo", "params": [60 + 7 * i]}
+        r["ttr"] = {"dist": "normal", "params": [3, 2]}
+    out["js20_breakdowns"] = dict(cfg=cfg, resources=res20b, products=prod20b, policy="base", seed=424242, patches=[])
+
+    sim, res, prod, _ = _example("toc_dbr")
+    sim.pop("print_mode", None)
+    sim.update(run_until=3001, warmup=600, memory_size=200000)
+    out["dbr_shipped"] = dict(cfg=sim, resources=res, products=prod, policy="dbr", seed=54907, patches=["P2"])
+    out["dbr_repaired"] = dict(cfg=dict(sim), resources=res, products=prod, policy="dbr", seed=54907,
+                               patches=["P2", "P3"])
+    return out
+
+
+def write_examples():
+    for name in ("simple_scheduler", "toc_dbr"):
+        sim, res, prod, exp = rr.load_example(name)
+        blob = {"simulation": sim, "resources": res, "products": prod, "experiment": exp,
+                "source": f"/root/reference/examples/{name} (config.yaml + products + resources), dumped by oracle/gen_golden.py"}
+        (GOLDEN / f"example_{name}.json").write_text(json.dumps(blob, separators=(",", ":")))
+
+
+def write_variate_kat():
+    """Known-answer vectors from the reference's own DistributionGenerator (engine/utils.py:21-105)."""
+    DG = rr.load_reference()["utils"].DistributionGenerator
+    cases = [("erlang", [10, 5.77, 3]), ("uniform", [10, 5.77, 0]), ("expo", [4635]), ("normal", [5.24, 2.97]),
+             ("gamma", [0.78, 0.45]), ("constant", [63]), ("normal", [0.04, 0.05]), ("constant", [0, 0])]
+    batch = [("gamma", [0.78, 0.45], 1), ("gamma", [0.78, 0.45], 5), ("expo", [2.0], 3), ("normal", [1.0, 2.0], 4),
+             ("uniform", [10, 5.77], 2), ("constant", [0.78], 3), ("erlang", [1.2, 0.7], 0)]
+    kat = {"scalar": [], "batch": [], "run_seeds": {}}
+    for seed in (42, 54907):
+        g = DG(seed)
+        for _ in range(3):
+            for dist, params in cases:
+                v = g.random_number(dist, params)
+                kat["scalar"].append({"seed": seed, "dist": dist, "params": params, "value": float(v),
+                                      "is_int": isinstance(v, int)})
+        g = DG(seed)
+        for _ in range(2):
+            for dist, params, n in batch:
+                kat["batch"].append({"seed": seed, "dist": dist, "params": params, "count": n,
+                                     "value": g.sum_random_numbers_batch(dist, params, n)})
+    for seed in (123, 20260101):
+        g = DG(seed)
+        kat["run_seeds"][str(seed)] = [g.random_int() for _ in range(8)]
+    (GOLDEN / "variates_kat.json").write_text(json.dumps(kat, indent=0))
+
+
+def generate(name, spec):
+    out = rr.run_reference(spec["cfg"], spec["resources"], spec["products"], spec["seed"],
+                           policy=spec["policy"], patches=spec["patches"])
+    scen = {k: spec[k] for k in ("cfg", "resources", "products", "policy", "seed", "patches")}
+    sim = out["sim"]
+    metrics = {"products": sim.products_metrics().to_dict(orient="list"),
+               "resources": sim.resources_metrics().to_dict(orient="list"),
+               "general": sim.general_metrics().to_dict(orient="list")}
+    np.savez_compressed(
+        GOLDEN / f"{name}.npz",
+        ring=out["ring"], time=out["time"], value=out["value"],
+        tape_A=out["tape_A"], tape_B=out["tape_B"], tape_C=out["tape_C"], tape_D=out["tape_D"],
+        steps=np.int64(out["steps"]), error=np.str_(out["error"] or ""),
+        scenario=np.str_(json.dumps(scen)), metrics=np.str_(json.dumps(metrics)),
+        now=np.float64(out["now"]), now_is_int=np.bool_(isinstance(out["now"], int)))
+    print(f"{name}: steps={out['steps']} records={len(out['ring'])} tapes="
+          f"{len(out['tape_A'])}/{len(out['tape_B'])}/{len(out['tape_C'])}/{len(out['tape_D'])} "
+          f"error={out['error']}")
+
+
+def main(argv):
+    GOLDEN.mkdir(parents=True, exist_ok=True)
+    write_examples()
+    write_variate_kat()
+    table = scenario_table()
+    for name in (argv or table.keys()):
+        generate(name, table[name])
+
+
+if __name__ == "__main__":
+    main(sys.argv[1:])

@@ -1,0 +1,174 @@
+"""Host compiler: reference-schema Mappings -> flat structure-of-arrays scenario tables.
+
+Replaces the per-event dict walks of the reference (stores.py:22-30 routing lists; factory_sim.py:144-152
+demand triplets, :249-260 TBF, :404-410 setup, :425-430 processing time) with tables built once per scenario.
+Accepts plain dicts or any Mapping with ``.get`` / ``.keys`` / ``[]`` (OmegaConf DictConfig included).
+Mapping order is preserved everywhere: it defines entity indices, initial eids and the initial TBF draw order.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass, field
+from typing import Any, List, Mapping
+
+import numpy as np
+
+DIST_KINDS = {"constant": 0, "uniform": 1, "gamma": 2, "erlang": 3, "expo": 4, "normal": 5}
+DELIVERY_MODES = {"asReady": 0, "onDue": 1, "instantly": 2}
+POLICIES = {"fifo": 0, "max_priority": 1, "dbr": 2}
+
+PRODUCT_METRICS = ["deliveredOntime", "deliveredLate", "lostSales", "flowTime", "leadTime", "tardiness",
+                   "earliness", "wip", "finishedGoods", "totalInventory", "released"]
+RESOURCE_METRICS = ["utilization", "breakdown", "setup", "queue"]
+GENERAL_METRICS = ["wip_general", "finishedGoods_general", "totalInventory_general"]
+SUM_METRICS = {"deliveredOntime", "deliveredLate", "lostSales", "utilization", "breakdown", "setup"}
+TIME_NORMALIZED = {"utilization", "breakdown", "setup"}
+
+
+@dataclass
+class Dist:
+    kind: int
+    raw0: float
+    raw1: float
+    d0: float
+    d1: float
+
+
+def compile_dist(cfg: Mapping | None, default_dist=None, default_params=None) -> Dist:
+    """(dist, params) -> kind + derived float64 parameters, with the reference's exact expressions
+    (engine/utils.py:8-18); unknown names raise the reference's ValueError (utils.py:65)."""
+    if cfg is None:
+        return Dist(-1, 0.0, 0.0, 0.0, 0.0)
+    dist = cfg.get("dist", default_dist)
+    params = cfg.get("params", default_params)
+    if dist not in DIST_KINDS:
+        raise ValueError(f"Unknowh distribution type {dist}")
+    params = list(params)
+    p0 = float(params[0])
+    p1 = float(params[1]) if len(params) > 1 else 0.0
+    if dist == "constant":
+        d0, d1 = p0, 0.0
+    elif dist == "uniform":
+        c = params[1] * 2 * np.sqrt(3)
+        d0, d1 = float(params[0] - (c / 2)), float(params[0] + (c / 2))
+    elif dist in ("gamma", "erlang"):
+        d0, d1 = float(params[0] ** 2 / params[1] ** 2), float(params[1] ** 2 / params[0])
+    elif dist == "expo":
+        d0, d1 = p0, 0.0
+    else:  # normal
+        d0, d1 = p0, p1
+    return Dist(DIST_KINDS[dist], p0, p1, d0, d1)
+
+
+@dataclass
+class ScenarioTables:
+    resource_names: List[str]
+    product_names: List[str]
+    route_start: np.ndarray
+    step_resource: np.ndarray
+    step_time: List[Dist]
+    res_setup: List[Dist]
+    res_tbf: List[Dist]
+    res_ttr: List[Dist]
+    prod_freq: List[Dist]
+    prod_qty: List[Dist]
+    prod_due: List[Dist]
+    shipping_buffer: np.ndarray
+    run_until: Any
+    warmup: Any
+    delivery_mode: int
+    policy: int
+    log_queues: bool
+    dbr: dict = field(default_factory=dict)
+    max_production_orders: int = 0
+    max_demand_orders: int = 0
+    fifo_capacity: int = 0
+
+    @property
+    def R(self):
+        return len(self.resource_names)
+
+    @property
+    def P(self):
+        return len(self.product_names)
+
+    @property
+    def n_rings(self):
+        return 11 * self.P + 4 * self.R + 3
+
+    def ring_names(self):
+        """[(variable, key)] in ring-id order."""
+        out = [(m, p) for m in PRODUCT_METRICS for p in self.product_names]
+        out += [(m, r) for m in RESOURCE_METRICS for r in self.resource_names]
+        out += [(m, "general") for m in GENERAL_METRICS]
+        return out
+
+
+def compile_scenario(config: Mapping, resources: Mapping, products: Mapping, policy: str = "fifo",
+                     dbr_repair: bool = False, max_production_orders: int = 0, max_demand_orders: int = 0,
+                     fifo_capacity: int = 0) -> ScenarioTables:
+    run_until = config.get("run_until", None)
+    if run_until is None:
+        raise ValueError("run_until must be specified")            # factory_sim.py:40-42
+    warmup = config.get("warmup", 0)
+    mode = config.get("delivery_mode", "asReady")
+    if mode not in DELIVERY_MODES:
+        raise ValueError(f"unknown delivery_mode {mode!r}")
+    if policy not in POLICIES:
+        raise NotImplementedError(f"unknown policy {policy!r}")
+    if config.get("enable_event_logging", True) and not config.get("allocate_log_storage", True):
+        raise ValueError("allocate_log_storage=False with event logging enabled is rejected (reference IndexError, E16)")
+    rnames = list(resources.keys())
+    pnames = list(products.keys())
+    route_start = [0]
+    step_res, step_time = [], []
+    for p in pnames:
+        procs = products[p].get("processes")
+        for st in procs.values():
+            step_res.append(rnames.index(st["resource"]))
+            step_time.append(compile_dist(st["processing_time"]))
+        route_start.append(len(step_res))
+    res_setup, res_tbf, res_ttr = [], [], []
+    for r in rnames:
+        rc = resources[r]
+        res_setup.append(compile_dist(rc["setup"], "constant", [0]))   # mandatory key (factory_sim.py:404)
+        tbf = rc.get("tbf", None)
+        res_tbf.append(compile_dist(tbf, "constant", [0]) if tbf else compile_dist(None))
+        res_ttr.append(compile_dist(rc["ttr"], "constant", [0]) if tbf else compile_dist(None))
+    pf, pq, pd_ = [], [], []
+    for p in pnames:
+        dm = products[p]["demand"]
+        pf.append(compile_dist(dm["freq"]))
+        pq.append(compile_dist(dm["quantity"]))
+        pd_.append(compile_dist(dm["duedate"]))
+    ship = np.array([float(products[p].get("shipping_buffer", 0)) for p in pnames], dtype=np.float64)
+    t = ScenarioTables(rnames, pnames, np.array(route_start, dtype=np.int32), np.array(step_res, dtype=np.int32),
+                       step_time, res_setup, res_tbf, res_ttr, pf, pq, pd_, ship, run_until, warmup,
+                       DELIVERY_MODES[mode], POLICIES[policy], bool(config.get("log_queues", False)),
+                       max_production_orders=max_production_orders, max_demand_orders=max_demand_orders,
+                       fifo_capacity=fifo_capacity)
+    if policy == "dbr":
+        t.dbr = _compile_dbr(config, resources, products, t, dbr_repair)
+    return t
+
+
+def _compile_dbr(config, resources, products, t: ScenarioTables, repair: bool) -> dict:
+    """DBRSimulation constructor state (examples/toc_dbr/simulation.py:29-35, 146-171, 201-204)."""
+    P, R = t.P, t.R
+    load = np.zeros((P, R), dtype=np.float32)
+    for p, name in enumerate(t.product_names):
+        dm = products[name]["demand"]
+        gap = dm["freq"]["params"][0]
+        qty = dm["quantity"]["params"][0]
+        for s in range(t.route_start[p], t.route_start[p + 1]):
+            load[p, t.step_resource[s]] += t.step_time[s].raw0
+        load[p, :] = load[p, :] * (1 / gap) * qty
+    ccr = int(np.argsort(-load.sum(axis=0), kind="stable")[0])
+    ccr_setup = resources[t.resource_names[ccr]].get("setup", {"params": None}).get("params", [0])[0]
+    ccr_pt = np.array([sum([t.step_time[s].raw0 for s in range(t.route_start[p], t.route_start[p + 1])
+                            if t.step_resource[s] == ccr]) for p in range(P)], dtype=np.float64)
+    interval = config.get("scheduler_interval", 72)
+    return {"ccr": ccr, "ccr_setup": float(ccr_setup), "ccr_pt": ccr_pt, "repair": bool(repair),
+            "interval": interval, "cb_target": float(config.get("cb_target_level", float("inf"))),
+            "release_limit": float(config.get("order_release_limit", float("inf"))),
+            "ccr_limit": float(config.get("ccr_release_limit", False) or 0.0),
+            "min_lot": float(config.get("min_lotsize", 0))}

@@ -1,0 +1,402 @@
+// msim_api.cu -- host side of the C ABI declared in include/msim.h.
+//
+// msim_create compiles the scenario tables into (a) one block-shared table blob that every CTA stages into
+// shared memory and (b) the byte layout of the per-replication shared-memory slab; it then sizes the launch as a
+// persistent grid of  n_SMs x resident-CTAs-per-SM  blocks whose warps pull replication indices from a global
+// counter (replications have very different lengths, so static striping would leave a long tail).
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdio.h>
+#include <string.h>
+#include <string>
+#include <vector>
+#include "msim_device.cuh"
+
+using namespace msim;
+
+static thread_local std::string g_err;
+static int fail(int code, const std::string& msg) { g_err = msg; return code; }
+#define CU(expr)                                                                                       \
+    do {                                                                                               \
+        cudaError_t e_ = (expr);                                                                       \
+        if (e_ != cudaSuccess) return fail(MSIM_E_CUDA, std::string(#expr) + ": " + cudaGetErrorString(e_)); \
+    } while (0)
+
+struct msim_handle_s {
+    KParams kp;                 // layout + scalar parameters (args filled per run)
+    int policy;
+    int n_sms;
+    int warps_per_block;
+    int blocks_per_sm[2];       // per rng mode
+    int regs[2];
+    size_t smem_bytes;
+    unsigned char* d_tables;
+    unsigned long long* d_counter;
+    double span;                // run_until - warmup
+    // scratch for msim_run_host
+    void* d_scratch; size_t scratch_bytes;
+    cudaEvent_t ev0, ev1;
+};
+
+static int align_up(int x, int a) { return (x + a - 1) / a * a; }
+
+static DDist to_ddist(const msim_dist_t& d) {
+    DDist o;
+    o.raw0 = d.raw0;
+    o.kind = d.kind;
+    o.pad = 0;
+    o.d0 = (float)d.d0;
+    o.d1 = (float)d.d1;
+    return o;
+}
+
+static const char* check_dist(const msim_dist_t& d, bool allow_none) {
+    if (d.kind == MSIM_DIST_NONE) return allow_none ? nullptr : "missing distribution";
+    if (d.kind < 0 || d.kind > MSIM_DIST_NORMAL) return "Unknowh distribution type";   // utils.py:65 (sic)
+    return nullptr;
+}
+
+extern "C" int msim_version(void) { return MSIM_VERSION; }
+extern "C" const char* msim_last_error(void) { return g_err.c_str(); }
+
+extern "C" int msim_create(const msim_tables_t* t, msim_handle_t* out) {
+    if (!t || !out) return fail(MSIM_E_INVALID, "null argument");
+    const int R = t->n_resources, P = t->n_products, S = t->n_steps;
+    if (R < 1 || R > 32 || P < 1 || P > 32) return fail(MSIM_E_UNSUPPORTED, "need 1 <= R <= 32 and 1 <= P <= 32");
+    if (S < P || S > 4096) return fail(MSIM_E_INVALID, "bad n_steps");
+    if (!(t->run_until > 0.0) || !(t->run_until > t->warmup) || t->warmup < 0.0)
+        return fail(MSIM_E_INVALID, "need 0 <= warmup < run_until");
+    if (t->delivery_mode < 0 || t->delivery_mode > 2) return fail(MSIM_E_INVALID, "bad delivery_mode");
+    if (t->policy != MSIM_POLICY_FIFO && t->policy != MSIM_POLICY_MAX_PRIORITY && t->policy != MSIM_POLICY_DBR)
+        return fail(MSIM_E_INVALID, "bad policy");
+    for (int p = 0; p < P; ++p) {
+        int n = t->route_start[p + 1] - t->route_start[p];
+        if (n < 1 || n > 250) return fail(MSIM_E_INVALID, "every product needs 1..250 route steps");
+        const char* e;
+        if ((e = check_dist(t->prod_freq[p], false)) || (e = check_dist(t->prod_qty[p], false)) ||
+            (e = check_dist(t->prod_due[p], false)))
+            return fail(MSIM_E_INVALID, e);
+    }
+    if (t->route_start[0] != 0 || t->route_start[P] != S) return fail(MSIM_E_INVALID, "route_start must span [0,S]");
+    for (int s = 0; s < S; ++s) {
+        if (t->step_resource[s] < 0 || t->step_resource[s] >= R) return fail(MSIM_E_INVALID, "step_resource out of range");
+        if (const char* e = check_dist(t->step_time[s], false)) return fail(MSIM_E_INVALID, e);
+    }
+    for (int r = 0; r < R; ++r) {
+        const char* e;
+        if ((e = check_dist(t->res_setup[r], false)) || (e = check_dist(t->res_tbf[r], true)))
+            return fail(MSIM_E_INVALID, e);
+        if (t->res_tbf[r].kind != MSIM_DIST_NONE && (e = check_dist(t->res_ttr[r], false)))
+            return fail(MSIM_E_INVALID, "ttr is required when tbf is configured");
+    }
+
+    msim_handle_s* h = new msim_handle_s();
+    memset(&h->kp, 0, sizeof(h->kp));
+    h->policy = t->policy;
+    h->d_scratch = nullptr; h->scratch_bytes = 0;
+    Lay& L = h->kp.lay;
+    L.R = R; L.P = P; L.S = S;
+    L.NT = align_up(R + P + 2, 32);
+    L.MP = t->max_production_orders > 0 ? t->max_production_orders : 96;
+    L.MD = t->max_demand_orders > 0 ? t->max_demand_orders : 96;
+    L.NQ = t->fifo_capacity > 0 ? t->fifo_capacity : 64;
+    L.UQ = 16;
+    if (L.MP > 250 || L.MD > 250 || (L.NQ & (L.NQ - 1))) { delete h; return fail(MSIM_E_INVALID, "bad pool capacities"); }
+    L.K = 11 * P + 4 * R + 3;
+    const bool dbr = t->policy == MSIM_POLICY_DBR;
+    const bool prio = t->policy != MSIM_POLICY_FIFO;
+    const bool on_due = t->delivery_mode == MSIM_DELIVERY_ON_DUE;
+
+    // ---- per-replication slab layout
+    int off = 0;
+    auto take = [&](int bytes, int align) { off = align_up(off, align); int o = off; off += bytes; return o; };
+    L.stage = take(kStageCap * 16, 16);
+    L.nq = take(L.NQ * 4, 4);
+    L.uq = take(L.UQ * 4, 4);
+    L.tm_time = take(L.NT * 4, 4);
+    L.tm_eid = take(L.NT * 4, 4);
+    L.r_utf = take(R * 4, 4); L.r_tbf = take(R * 4, 4); L.r_setup = take(R * 4, 4); L.r_start = take(R * 4, 4);
+    L.r_busy = take(R * 4, 4); L.r_qq = take(R * 4, 4); L.r_lastq = take(R * 4, 4);
+    L.p_fg = take(P * 4, 4); L.p_wip = take(P * 4, 4); L.p_fgc = take(P * 4, 4); L.p_dqty = take(P * 4, 4);
+    L.p_ddue = take(P * 4, 4);
+    L.po_rel = take(L.MP * 4, 4); L.po_qty = take(L.MP * 4, 4);
+    L.po_prio = prio ? take(L.MP * 4, 4) : 0;
+    L.po_tt = dbr ? take(L.MP * 4, 4) : 0; L.po_eid = dbr ? take(L.MP * 4, 4) : 0; L.po_ccr = dbr ? take(L.MP * 4, 4) : 0;
+    L.do_arr = take(L.MD * 4, 4); L.do_due = take(L.MD * 4, 4); L.do_qty = take(L.MD * 4, 4);
+    L.do_tt = take(L.MD * 4, 4);               // kept for every mode: the calendar scan reads it only for onDue
+    L.do_eid = on_due ? take(L.MD * 4, 4) : 0;
+    L.r_phase = take(R, 1); L.r_cur = take(R, 1); L.r_tcur = take(R, 1);
+    L.r_inh = take(R, 1); L.r_int = take(R, 1); L.r_outh = take(R, 1); L.r_outt = take(R, 1);
+    L.p_obh = take(P, 1); L.p_obt = take(P, 1); L.p_fgqh = take(P, 1); L.p_fgqt = take(P, 1);
+    L.po_prod = take(L.MP, 1); L.po_done = take(L.MP, 1); L.po_next = take(L.MP, 1); L.po_loc = take(L.MP, 1);
+    L.do_prod = take(L.MD, 1); L.do_next = take(L.MD, 1);
+    L.scal = take((int)sizeof(Scal), 8);
+    L.slab_bytes = align_up(off, 16);
+
+    // ---- block-shared table blob
+    std::vector<unsigned char> blob;
+    auto put = [&](const void* src, size_t bytes, size_t align) {
+        size_t o = (blob.size() + align - 1) / align * align;
+        blob.resize(o + bytes);
+        memcpy(blob.data() + o, src, bytes);
+        return (int)o;
+    };
+    {
+        std::vector<uint16_t> rs(P + 1);
+        for (int p = 0; p <= P; ++p) rs[p] = (uint16_t)t->route_start[p];
+        std::vector<uint8_t> sr(S);
+        for (int s = 0; s < S; ++s) sr[s] = (uint8_t)t->step_resource[s];
+        std::vector<DDist> sd(S), su(R), tb(R), tr(R), fq(P), qt(P), du(P);
+        for (int s = 0; s < S; ++s) sd[s] = to_ddist(t->step_time[s]);
+        for (int r = 0; r < R; ++r) {
+            su[r] = to_ddist(t->res_setup[r]);
+            tb[r] = to_ddist(t->res_tbf[r]);
+            msim_dist_t none; memset(&none, 0, sizeof(none)); none.kind = MSIM_DIST_CONSTANT;
+            tr[r] = to_ddist(t->res_tbf[r].kind == MSIM_DIST_NONE ? none : t->res_ttr[r]);
+        }
+        for (int p = 0; p < P; ++p) {
+            fq[p] = to_ddist(t->prod_freq[p]); qt[p] = to_ddist(t->prod_qty[p]); du[p] = to_ddist(t->prod_due[p]);
+        }
+        std::vector<double> sbuf(P, 0.0), cpt(P, 0.0);
+        for (int p = 0; p < P; ++p) {
+            if (t->prod_shipping_buffer) sbuf[p] = t->prod_shipping_buffer[p];
+            if (t->dbr_ccr_pt) cpt[p] = t->dbr_ccr_pt[p];
+        }
+        L.t_step_dist = put(sd.data(), sd.size() * sizeof(DDist), 8);
+        L.t_setup = put(su.data(), su.size() * sizeof(DDist), 8);
+        L.t_tbf = put(tb.data(), tb.size() * sizeof(DDist), 8);
+        L.t_ttr = put(tr.data(), tr.size() * sizeof(DDist), 8);
+        L.t_freq = put(fq.data(), fq.size() * sizeof(DDist), 8);
+        L.t_qty = put(qt.data(), qt.size() * sizeof(DDist), 8);
+        L.t_due = put(du.data(), du.size() * sizeof(DDist), 8);
+        L.t_shipbuf = put(sbuf.data(), sbuf.size() * 8, 8);
+        L.t_ccrpt = put(cpt.data(), cpt.size() * 8, 8);
+        L.t_route_start = put(rs.data(), rs.size() * 2, 2);
+        L.t_step_res = put(sr.data(), sr.size(), 1);
+        blob.resize((blob.size() + 15) / 16 * 16);
+        L.t_bytes = (int)blob.size();
+    }
+
+    KParams& kp = h->kp;
+    kp.run_until = (float)t->run_until;
+    kp.warmup = (float)t->warmup;
+    kp.delivery_mode = t->delivery_mode;
+    kp.log_queues = t->log_queues ? 1 : 0;
+    kp.dbr_ccr = t->dbr_ccr; kp.dbr_repair = t->dbr_repair;
+    kp.dbr_interval = t->dbr_interval; kp.dbr_cb_target = t->dbr_cb_target; kp.dbr_release_limit = t->dbr_release_limit;
+    kp.dbr_ccr_limit = t->dbr_ccr_limit; kp.dbr_min_lot = t->dbr_min_lot; kp.dbr_ccr_setup = t->dbr_ccr_setup;
+    h->span = t->run_until - t->warmup;
+
+    int dev = 0;
+    cudaDeviceProp prop;
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaGetDeviceProperties(&prop, dev) != cudaSuccess) {
+        delete h;
+        return fail(MSIM_E_CUDA, "no CUDA device: libmsim has no CPU fallback");
+    }
+    h->n_sms = prop.multiProcessorCount;
+    // warps per block: as many replications per SM as shared memory allows, in CTAs of <= 8 warps
+    const size_t smem_sm = prop.sharedMemPerMultiprocessor;            // 228 KB on B200
+    const size_t smem_blk_max = prop.sharedMemPerBlockOptin;           // 227 KB
+    int best_w = 1, best_total = 0;
+    for (int w = 1; w <= 8; ++w) {
+        size_t need = (size_t)L.t_bytes + (size_t)w * L.slab_bytes;
+        if (need > smem_blk_max) break;
+        int nblk = (int)(smem_sm / (need + 1024));                     // 1 KB per-CTA reservation
+        if (nblk < 1) continue;
+        int warps = nblk * w;
+        if (warps > 64) warps = 64;
+        if (warps > best_total || (warps == best_total && w > best_w)) { best_total = warps; best_w = w; }
+    }
+    if (best_total == 0) { delete h; return fail(MSIM_E_UNSUPPORTED, "scenario does not fit shared memory"); }
+    h->warps_per_block = best_w;
+    kp.warps_per_block = best_w;
+    h->smem_bytes = (size_t)L.t_bytes + (size_t)best_w * L.slab_bytes;
+    for (int rng = 0; rng < 2; ++rng) {
+        int rc = sim_kernel_attrs(h->policy, rng, h->smem_bytes, &h->regs[rng], best_w * 32, &h->blocks_per_sm[rng]);
+        if (rc != 0) {
+            delete h;
+            return fail(rc, rc == MSIM_E_UNSUPPORTED ? "policy not available in this build" : "kernel attribute query failed");
+        }
+        if (h->blocks_per_sm[rng] < 1) { delete h; return fail(MSIM_E_UNSUPPORTED, "kernel cannot be resident"); }
+    }
+    if (cudaMalloc(&h->d_tables, blob.size()) != cudaSuccess || cudaMalloc(&h->d_counter, 8) != cudaSuccess) {
+        delete h;
+        return fail(MSIM_E_NOMEM, "cudaMalloc failed");
+    }
+    CU(cudaMemcpy(h->d_tables, blob.data(), blob.size(), cudaMemcpyHostToDevice));
+    kp.tables = h->d_tables;
+    kp.work_counter = h->d_counter;
+    CU(cudaEventCreate(&h->ev0));
+    CU(cudaEventCreate(&h->ev1));
+    *out = h;
+    return 0;
+}
+
+extern "C" int msim_destroy(msim_handle_t h) {
+    if (!h) return 0;
+    cudaFree(h->d_tables);
+    cudaFree(h->d_counter);
+    if (h->d_scratch) cudaFree(h->d_scratch);
+    cudaEventDestroy(h->ev0);
+    cudaEventDestroy(h->ev1);
+    delete h;
+    return 0;
+}
+
+extern "C" int msim_query(msim_handle_t h, msim_info_t* info) {
+    if (!h || !info) return fail(MSIM_E_INVALID, "null argument");
+    const Lay& L = h->kp.lay;
+    info->n_rings = L.K;
+    info->smem_per_replication = L.slab_bytes;
+    info->smem_tables = L.t_bytes;
+    info->warps_per_block = h->warps_per_block;
+    info->blocks_per_sm = h->blocks_per_sm[0];
+    info->n_sms = h->n_sms;
+    info->regs_per_thread = h->regs[0];
+    info->max_production_orders = L.MP;
+    info->max_demand_orders = L.MD;
+    info->fifo_capacity = L.NQ;
+    return 0;
+}
+
+extern "C" int msim_run(msim_handle_t h, const msim_run_args_t* a) {
+    if (!h || !a) return fail(MSIM_E_INVALID, "null argument");
+    if (a->n_reps <= 0) return 0;
+    if (!a->acc_sum || !a->acc_cnt || !a->n_events || !a->status) return fail(MSIM_E_INVALID, "missing output buffer");
+    if (a->rng_mode != MSIM_RNG_PHILOX && a->rng_mode != MSIM_RNG_REPLAY) return fail(MSIM_E_INVALID, "bad rng_mode");
+    if (a->rng_mode == MSIM_RNG_REPLAY &&
+        (!a->tape_A || !a->tape_B || !a->tape_C || !a->tape_D || !a->tape_A_off || !a->tape_B_off || !a->tape_C_off ||
+         !a->tape_D_off))
+        return fail(MSIM_E_INVALID, "replay mode needs the four tapes and their offsets");
+    if (a->log && (a->log_cap <= 0 || !a->log_count)) return fail(MSIM_E_INVALID, "log ring needs log_cap > 0 and log_count");
+    KParams kp = h->kp;
+    kp.a = *a;
+    if (!a->log) { kp.a.n_log_reps = 0; }
+    cudaStream_t st = (cudaStream_t)a->stream;
+    CU(cudaMemsetAsync(h->d_counter, 0, 8, st));
+    const int rng = a->rng_mode;
+    long long blocks_needed = (a->n_reps + h->warps_per_block - 1) / h->warps_per_block;
+    long long grid = (long long)h->n_sms * h->blocks_per_sm[rng];
+    if (grid > blocks_needed) grid = blocks_needed;
+    int rc = launch_sim(kp, h->policy, rng, (int)grid, h->warps_per_block * 32, h->smem_bytes, st);
+    if (rc != 0) return fail(rc, std::string("kernel launch failed: ") + cudaGetErrorString(cudaGetLastError()));
+    return 0;
+}
+
+extern "C" int msim_reduce_metrics(msim_handle_t h, const double* acc_sum, const uint32_t* acc_cnt, const int32_t* status,
+                                   int64_t n_reps, double* out, void* stream) {
+    if (!h || !acc_sum || !acc_cnt || !status || !out) return fail(MSIM_E_INVALID, "null argument");
+    const Lay& L = h->kp.lay;
+    int rc = launch_reduce(acc_sum, acc_cnt, status, n_reps, L.K, L.P, L.R, h->span, out, stream);
+    if (rc != 0) return fail(rc, "reduce launch failed");
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// host-buffer path: stage inputs, run, copy results back (the e2e leg of bench.py and the ctypes default)
+extern "C" int msim_run_host(msim_handle_t h, const msim_host_args_t* a) {
+    if (!h || !a) return fail(MSIM_E_INVALID, "null argument");
+    if (a->n_reps <= 0) return 0;
+    const Lay& L = h->kp.lay;
+    const int64_t n = a->n_reps;
+    const bool replay = a->rng_mode == MSIM_RNG_REPLAY;
+    int64_t la = 0, lb = 0, lc = 0, ld = 0;
+    if (replay) {
+        if (!a->tape_A_off || !a->tape_B_off || !a->tape_C_off || !a->tape_D_off)
+            return fail(MSIM_E_INVALID, "replay mode needs tape offsets");
+        la = a->tape_A_off[n]; lb = a->tape_B_off[n]; lc = a->tape_C_off[n]; ld = a->tape_D_off[n];
+    }
+    const bool logs = a->log && a->n_log_reps > 0 && a->log_cap > 0;
+    const int64_t nlog = logs ? (a->n_log_reps < n ? a->n_log_reps : n) : 0;
+    // carve one scratch allocation
+    size_t off = 0;
+    auto carve = [&](size_t bytes) { off = (off + 255) / 256 * 256; size_t o = off; off += bytes; return o; };
+    size_t o_sum = carve((size_t)n * L.K * 8), o_cnt = carve((size_t)n * L.K * 4), o_ev = carve((size_t)n * 8),
+           o_to = carve((size_t)n * 4), o_st = carve((size_t)n * 4), o_seed = carve((size_t)n * 8),
+           o_ta = carve((size_t)la * 4), o_tb = carve((size_t)lb * 4), o_tc = carve((size_t)lc * 8), o_td = carve((size_t)ld * 4),
+           o_oa = carve((size_t)(n + 1) * 8), o_ob = carve((size_t)(n + 1) * 8), o_oc = carve((size_t)(n + 1) * 8),
+           o_od = carve((size_t)(n + 1) * 8), o_log = carve((size_t)nlog * (size_t)a->log_cap * 16),
+           o_lc = carve((size_t)(nlog ? nlog : 1) * 4);
+    size_t total = carve(0);
+    if (total > h->scratch_bytes) {
+        if (h->d_scratch) cudaFree(h->d_scratch);
+        h->d_scratch = nullptr; h->scratch_bytes = 0;
+        if (cudaMalloc(&h->d_scratch, total) != cudaSuccess) return fail(MSIM_E_NOMEM, "scratch cudaMalloc failed");
+        h->scratch_bytes = total;
+    }
+    unsigned char* base = (unsigned char*)h->d_scratch;
+    cudaStream_t st = 0;
+    msim_run_args_t r;
+    memset(&r, 0, sizeof(r));
+    r.n_reps = n; r.rep_offset = a->rep_offset; r.rng_mode = a->rng_mode; r.philox_seed = a->philox_seed;
+    if (a->rep_seeds) {
+        CU(cudaMemcpyAsync(base + o_seed, a->rep_seeds, (size_t)n * 8, cudaMemcpyHostToDevice, st));
+        r.rep_seeds = (const uint64_t*)(base + o_seed);
+    }
+    if (replay) {
+        CU(cudaMemcpyAsync(base + o_ta, a->tape_A, (size_t)la * 4, cudaMemcpyHostToDevice, st));
+        CU(cudaMemcpyAsync(base + o_tb, a->tape_B, (size_t)lb * 4, cudaMemcpyHostToDevice, st));
+        CU(cudaMemcpyAsync(base + o_tc, a->tape_C, (size_t)lc * 8, cudaMemcpyHostToDevice, st));
+        CU(cudaMemcpyAsync(base + o_td, a->tape_D, (size_t)ld * 4, cudaMemcpyHostToDevice, st));
+        CU(cudaMemcpyAsync(base + o_oa, a->tape_A_off, (size_t)(n + 1) * 8, cudaMemcpyHostToDevice, st));
+        CU(cudaMemcpyAsync(base + o_ob, a->tape_B_off, (size_t)(n + 1) * 8, cudaMemcpyHostToDevice, st));
+        CU(cudaMemcpyAsync(base + o_oc, a->tape_C_off, (size_t)(n + 1) * 8, cudaMemcpyHostToDevice, st));
+        CU(cudaMemcpyAsync(base + o_od, a->tape_D_off, (size_t)(n + 1) * 8, cudaMemcpyHostToDevice, st));
+        r.tape_A = (const float*)(base + o_ta); r.tape_B = (const float*)(base + o_tb);
+        r.tape_C = (const double*)(base + o_tc); r.tape_D = (const float*)(base + o_td);
+        r.tape_A_off = (const int64_t*)(base + o_oa); r.tape_B_off = (const int64_t*)(base + o_ob);
+        r.tape_C_off = (const int64_t*)(base + o_oc); r.tape_D_off = (const int64_t*)(base + o_od);
+    }
+    r.acc_sum = (double*)(base + o_sum); r.acc_cnt = (uint32_t*)(base + o_cnt);
+    r.n_events = (uint64_t*)(base + o_ev); r.n_timeouts = (uint32_t*)(base + o_to); r.status = (int32_t*)(base + o_st);
+    if (logs) {
+        r.log = (msim_record_t*)(base + o_log); r.log_count = (uint32_t*)(base + o_lc);
+        r.log_cap = a->log_cap; r.n_log_reps = nlog;
+        CU(cudaMemsetAsync(base + o_lc, 0, (size_t)nlog * 4, st));
+    }
+    r.stream = st;
+    CU(cudaEventRecord(h->ev0, st));
+    int rc = msim_run(h, &r);
+    if (rc != 0) return rc;
+    CU(cudaEventRecord(h->ev1, st));
+    if (a->acc_sum) CU(cudaMemcpyAsync(a->acc_sum, r.acc_sum, (size_t)n * L.K * 8, cudaMemcpyDeviceToHost, st));
+    if (a->acc_cnt) CU(cudaMemcpyAsync(a->acc_cnt, r.acc_cnt, (size_t)n * L.K * 4, cudaMemcpyDeviceToHost, st));
+    if (a->n_events) CU(cudaMemcpyAsync(a->n_events, r.n_events, (size_t)n * 8, cudaMemcpyDeviceToHost, st));
+    if (a->n_timeouts) CU(cudaMemcpyAsync(a->n_timeouts, r.n_timeouts, (size_t)n * 4, cudaMemcpyDeviceToHost, st));
+    if (a->status) CU(cudaMemcpyAsync(a->status, r.status, (size_t)n * 4, cudaMemcpyDeviceToHost, st));
+    if (logs) {
+        CU(cudaMemcpyAsync(a->log, r.log, (size_t)nlog * (size_t)a->log_cap * 16, cudaMemcpyDeviceToHost, st));
+        if (a->log_count) CU(cudaMemcpyAsync(a->log_count, r.log_count, (size_t)nlog * 4, cudaMemcpyDeviceToHost, st));
+    }
+    CU(cudaStreamSynchronize(st));
+    if (a->kernel_ms) {
+        float ms = 0.f;
+        CU(cudaEventElapsedTime(&ms, h->ev0, h->ev1));
+        *a->kernel_ms = ms;
+    }
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+extern "C" int msim_test_philox(const uint32_t* ctr, const uint32_t* key, uint32_t* out, int64_t n) {
+    if (n <= 0) return 0;
+    uint32_t *dc = nullptr, *dk = nullptr, *dout = nullptr;
+    CU(cudaMalloc(&dc, n * 16)); CU(cudaMalloc(&dk, n * 8)); CU(cudaMalloc(&dout, n * 16));
+    CU(cudaMemcpy(dc, ctr, n * 16, cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(dk, key, n * 8, cudaMemcpyHostToDevice));
+    int rc = launch_test_philox(dc, dk, dout, n);
+    if (rc == 0) CU(cudaMemcpy(out, dout, n * 16, cudaMemcpyDeviceToHost));
+    cudaFree(dc); cudaFree(dk); cudaFree(dout);
+    return rc == 0 ? 0 : fail(rc, "philox test launch failed");
+}
+
+extern "C" int msim_test_variates(const msim_dist_t* dist, uint64_t seed, int32_t stream_id, int32_t batch_count,
+                                  double* out, int64_t n) {
+    if (!dist || !out || n <= 0) return fail(MSIM_E_INVALID, "bad argument");
+    double* dout = nullptr;
+    CU(cudaMalloc(&dout, n * 8));
+    int rc = launch_test_variates(to_ddist(*dist), seed, stream_id, batch_count, dout, n);
+    if (rc == 0) CU(cudaMemcpy(out, dout, n * 8, cudaMemcpyDeviceToHost));
+    cudaFree(dout);
+    return rc == 0 ? 0 : fail(rc, "variates test launch failed");
+}

@@ -1,0 +1,84 @@
+// Shared declarations between the simulation kernel (msim_kernel.cu) and the host C ABI (msim_api.cu).
+#pragma once
+#include <stdint.h>
+#include "../../include/msim.h"
+
+namespace msim {
+
+constexpr int kWarp = 32;
+constexpr int kStageCap = 32;      // staged records per replication (one 128-bit record per lane on flush)
+constexpr int kStageFlushAt = 25;  // a single event emits at most 7 records
+constexpr uint32_t kNone = 0xFFu;
+
+// device-side distribution entry (block-shared table)
+struct DDist {
+    double raw0;   // params[0] in float64 (constant batch = count * raw0, utils.py:83-84)
+    float d0, d1;  // derived parameters rounded to float32 for the Philox samplers
+    int32_t kind;
+    int32_t pad;
+};
+
+// per-replication scalars that live in shared memory (only lane 0 touches them between warp syncs)
+struct Scal {
+    float tot_wip;          // _cached_total_wip           factory_sim.py:71,215,315
+    float fgc_sum;          // sum(_cached_total_fg)        factory_sim.py:578,589
+    uint32_t mach_wait;     // bit r: _production_system(r) blocked on resource_input[r].get()
+    uint32_t trans_wait;    // bit r: _transportation(r) blocked on resource_output[r].get()
+    uint32_t deliv_wait;    // bit p: _delivery_orders(p) blocked on outbound[p].get()
+    uint32_t log_count;     // records emitted and flushed so far
+    uint32_t draw[4];       // per-stream draw index (A,B,C,D)
+    uint32_t tlen[4];       // replay: tape lengths
+    const void* tbase[4];   // replay: tape base pointers of this replication
+    uint32_t k0, k1;        // Philox replication key
+    uint32_t n_timeouts;
+    uint8_t sched_wait;     // scheduler blocked on inbound.get()
+    uint8_t inb_head, inb_tail;   // inbound_demand_orders items (linked through do_next)
+    uint8_t po_free, do_free;     // free lists
+    uint8_t pad[3];
+    // DBR
+    double cb_level;
+    uint8_t fwd_wait, drain_wait, fin_head, fin_tail;
+    uint8_t pad2[4];
+};
+
+// byte offsets of every per-replication array inside the warp's shared-memory slab and of every table
+// inside the block-shared table blob.  Computed once per handle on the host.
+struct Lay {
+    int32_t R, P, S, NT, MP, MD, NQ, UQ, K;
+    // per-replication slab
+    int32_t stage, nq, uq, tm_time, tm_eid;
+    int32_t r_utf, r_tbf, r_setup, r_start, r_busy, r_qq, r_lastq;
+    int32_t p_fg, p_wip, p_fgc, p_dqty, p_ddue;
+    int32_t po_rel, po_qty, po_prio, po_tt, po_eid, po_ccr;
+    int32_t do_arr, do_due, do_qty, do_tt, do_eid;
+    int32_t r_phase, r_cur, r_tcur, r_inh, r_int, r_outh, r_outt;
+    int32_t p_obh, p_obt, p_fgqh, p_fgqt;
+    int32_t po_prod, po_done, po_next, po_loc, do_prod, do_next;
+    int32_t scal, slab_bytes;
+    // block-shared tables
+    int32_t t_route_start, t_step_res, t_step_dist, t_setup, t_tbf, t_ttr, t_freq, t_qty, t_due, t_shipbuf, t_ccrpt,
+        t_bytes;
+};
+
+struct KParams {
+    Lay lay;
+    const unsigned char* tables;   // device copy of the table blob (t_bytes)
+    unsigned long long* work_counter;
+    float run_until, warmup;       // float32 views (heap comparisons happen at float32 precision, Appendix B.1)
+    int32_t delivery_mode, log_queues;
+    // DBR
+    int32_t dbr_ccr, dbr_repair;
+    double dbr_interval, dbr_cb_target, dbr_release_limit, dbr_ccr_limit, dbr_min_lot, dbr_ccr_setup;
+    int32_t warps_per_block, _pad;
+    msim_run_args_t a;             // device pointers
+};
+
+// launchers implemented in msim_kernel.cu
+int launch_sim(const KParams& p, int policy, int rng_mode, int grid, int block, size_t smem, void* stream);
+int sim_kernel_attrs(int policy, int rng_mode, size_t smem, int* regs, int block, int* blocks_per_sm);
+int launch_reduce(const double* acc_sum, const uint32_t* acc_cnt, const int32_t* status, int64_t n_reps, int K, int P,
+                  int R, double span, double* out, void* stream);
+int launch_test_philox(const uint32_t* ctr, const uint32_t* key, uint32_t* out, int64_t n);
+int launch_test_variates(DDist d, uint64_t seed, int stream_id, int batch_count, double* out, int64_t n);
+
+} // namespace msim

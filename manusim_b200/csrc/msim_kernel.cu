@@ -1,0 +1,952 @@
+// msim_kernel.cu -- the batched factory-replication kernel for B200 (sm_100a).
+//
+// One WARP owns one replication.  Everything the reference keeps in SimPy objects lives in a per-warp slab of
+// shared memory (layout: msim_device.cuh `Lay`):
+//   * event calendar  : one (time f32, eid) slot per static process that can sleep on a Timeout
+//                       (R machines, P demand generators, warm-up, DBR tick) + per-order slots for onDue
+//                       delivery timers; the next event is picked by a warp-wide shuffle min-reduction over
+//                       (time, eid) -- SimPy's heap order (time, priority, eid) restricted to Timeouts;
+//   * zero-delay events: SimPy schedules every put/get/request completion as a heap event at `now`.  Because
+//                       eids only grow, those behave as two FIFOs (URGENT = process Initialize, NORMAL = the
+//                       rest).  Lane 0 drains them literally, one micro-event at a
+//                       time, so the (time, priority, eid) order -- and with it every tie-break -- is
+//                       reproduced by construction, and the count of pops equals Environment.step() calls;
+//   * stores           : resource_input / resource_output as linked lists through the order pool,
+//                       processing/transport as single slots, FG/WIP containers as float levels + a FIFO of
+//                       blocked getters (head-of-line blocking, SimPy Container semantics);
+//   * log staging      : 32 x 128-bit records, flushed by the whole warp with one st.global.v4 per lane into
+//                       the replication's HBM ring; the same flush folds the records into per-ring
+//                       (sum f64, count) accumulators (warm-up filtering happens at emission, as in the
+//                       reference).
+// Scheduling rules (FIFO / max-priority / DBR) are template parameters, so is the variate source
+// (Philox4x32-10 keyed by replication/stream/draw index, or replay of host-recorded tapes).
+//
+// Reference anchors are given next to each handler as file:line of /root/reference/src/manusim/factory_sim.py.
+#include <cuda_runtime.h>
+#include <math_constants.h>
+#include "msim_device.cuh"
+#include "philox.cuh"
+
+namespace msim {
+
+#define FULLMASK 0xFFFFFFFFu
+
+enum Op : uint32_t {
+    OP_NONE = 0,
+    OP_TO_WARMUP, OP_TO_DEMAND, OP_PUT_INBOUND, OP_SCHED_GOT, OP_PUT_OUTBOUND,
+    OP_INIT_RELEASE, OP_REL_PUT1, OP_REL_PUT2,
+    OP_MACH_GOT, OP_MACH_PUTPROC, OP_MACH_REQ, OP_TO_SETUP, OP_TO_PROC, OP_TO_TTR, OP_MACH_GOTPROC, OP_MACH_PUTOUT,
+    OP_TRANS_GOT, OP_TRANS_PUT, OP_TRANS_GOT2_FINAL, OP_TRANS_GOT2_NEXT, OP_TRANS_FGPUT, OP_TRANS_WIPGET,
+    OP_TRANS_PUTIN,
+    OP_DELIV_GOT, OP_INIT_SHIP, OP_TO_SHIP, OP_SHIP_GOT,
+};
+
+enum Phase : uint8_t { PH_SETUP = 0, PH_PROC = 1, PH_TTR = 2 };
+enum Loc : uint8_t { LOC_NONE = 0, LOC_IN = 1, LOC_PROC = 2, LOC_OUT = 3, LOC_TRANS = 4 };
+enum Req : int { REQ_ADVANCE = 0, REQ_FLUSH = 1, REQ_DONE = 2 };
+
+// product / resource / general metric indices (enum order of metrics.py:43-67)
+enum { PM_ONTIME = 0, PM_LATE, PM_LOST, PM_FLOW, PM_LEAD, PM_TARDY, PM_EARLY, PM_WIP, PM_FG, PM_INV, PM_RELEASED };
+enum { RM_UTIL = 0, RM_BREAKDOWN, RM_SETUP, RM_QUEUE };
+enum { GM_WIP = 0, GM_FG, GM_INV };
+
+__device__ __forceinline__ uint32_t EV(uint32_t op, uint32_t a, uint32_t b) { return op | (a << 8) | (b << 16); }
+
+// round(np.float32 x, 6)  (factory_sim.py:284,443)
+__device__ __forceinline__ float round6(float x) { return __fdiv_rn(rintf(__fmul_rn(x, 1e6f)), 1e6f); }
+
+template <int POLICY, int RNG>
+struct Sim {
+    const KParams& p;
+    unsigned char* sb;        // this warp's slab
+    const unsigned char* tb;  // block-shared tables
+    Scal* sc;
+    long long rep;
+    // ---- lane-0 state kept in registers
+    float now;
+    uint32_t warm;
+    uint32_t nqh, nqt, uqh, uqt;
+    uint32_t nstage, logc;
+    uint32_t nev, tseq, same_left;
+    int status;
+    uint32_t pending;
+
+    __device__ __forceinline__ Sim(const KParams& p_, unsigned char* sb_, const unsigned char* tb_)
+        : p(p_), sb(sb_), tb(tb_) { sc = reinterpret_cast<Scal*>(sb + p.lay.scal); }
+
+#define ARR(T, field) (reinterpret_cast<T*>(sb + p.lay.field))
+#define TAB(T, field) (reinterpret_cast<const T*>(tb + p.lay.field))
+
+    __device__ __forceinline__ int ringP(int m, int prod) const { return m * p.lay.P + prod; }
+    __device__ __forceinline__ int ringR(int m, int r) const { return 11 * p.lay.P + m * p.lay.R + r; }
+    __device__ __forceinline__ int ringG(int g) const { return 11 * p.lay.P + 4 * p.lay.R + g; }
+
+    // ------------------------------------------------------------------ event queues
+    __device__ __forceinline__ void pushN(uint32_t ev) {
+        ARR(uint32_t, nq)[nqt & (uint32_t)(p.lay.NQ - 1)] = ev;
+        nqt++;
+        if (nqt - nqh > (uint32_t)p.lay.NQ) status = MSIM_ST_FIFO_OVERFLOW;
+    }
+    __device__ __forceinline__ void pushU(uint32_t ev) {
+        ARR(uint32_t, uq)[uqt & (uint32_t)(p.lay.UQ - 1)] = ev;
+        uqt++;
+        if (uqt - uqh > (uint32_t)p.lay.UQ) status = MSIM_ST_FIFO_OVERFLOW;
+    }
+    // env.timeout(delay) issued by a static process that owns calendar slot `slot`
+    __device__ __forceinline__ void timer(int slot, float t, uint32_t ev) {
+        if (t == now) {
+            pushN(ev);   // lands on the current timestamp: larger eid than everything already pending
+        } else {
+            ARR(float, tm_time)[slot] = t;
+            ARR(uint32_t, tm_eid)[slot] = tseq++;
+        }
+    }
+
+    // ------------------------------------------------------------------ variates
+    __device__ __forceinline__ float draw_scalar(int stream, const DDist& d) {
+        uint32_t idx = sc->draw[stream]++;
+        float v;
+        if (RNG == MSIM_RNG_REPLAY) {
+            if (idx >= sc->tlen[stream]) { status = MSIM_ST_TAPE_EXHAUSTED; return 0.0f; }
+            v = __ldg(reinterpret_cast<const float*>(sc->tbase[stream]) + idx);
+        } else {
+            PhiloxStream s{sc->k0, sc->k1, (uint32_t)stream, idx};
+            v = draw_scalar_philox(s, d.kind, d.d0, d.d1);
+            if (p.a.rec_cap > 0 && (long long)idx < p.a.rec_cap) {
+                float* dst = stream == 0 ? p.a.rec_A : (stream == 1 ? p.a.rec_B : p.a.rec_D);
+                dst[rep * p.a.rec_cap + idx] = v;
+            }
+        }
+        return v;
+    }
+    __device__ __forceinline__ double draw_batch(const DDist& d, int count) {
+        uint32_t idx = sc->draw[2]++;
+        double v;
+        if (RNG == MSIM_RNG_REPLAY) {
+            if (idx >= sc->tlen[2]) { status = MSIM_ST_TAPE_EXHAUSTED; return 0.0; }
+            v = __ldg(reinterpret_cast<const double*>(sc->tbase[2]) + idx);
+        } else {
+            PhiloxStream s{sc->k0, sc->k1, 2u, idx};
+            v = draw_batch_philox(s, d.kind, d.d0, d.d1, d.raw0, count);
+            if (p.a.rec_cap > 0 && (long long)idx < p.a.rec_cap) p.a.rec_C[rep * p.a.rec_cap + idx] = v;
+        }
+        return v;
+    }
+
+    // ------------------------------------------------------------------ records (Logger.log, logs.py:44-66)
+    __device__ __forceinline__ void emit(int ring, float t, float v) {
+        ARR(uint4, stage)[nstage] = make_uint4(__float_as_uint(t), __float_as_uint(v), (uint32_t)ring, logc + nstage);
+        nstage++;
+    }
+    // _log_inventory_metrics, factory_sim.py:551-601 (caller checked warm)
+    __device__ __forceinline__ void inventory(int prod, bool with_wip, bool with_fg) {
+        float w = ARR(float, p_wip)[prod];
+        float f = ARR(float, p_fg)[prod];
+        if (with_wip) {
+            emit(ringP(PM_WIP, prod), now, w);
+            emit(ringG(GM_WIP), now, sc->tot_wip);
+        }
+        if (with_fg) {
+            float old = ARR(float, p_fgc)[prod];
+            ARR(float, p_fgc)[prod] = f;
+            sc->fgc_sum = __fadd_rn(sc->fgc_sum, __fsub_rn(f, old));
+            emit(ringP(PM_FG, prod), now, f);
+            emit(ringG(GM_FG), now, sc->fgc_sum);
+        }
+        emit(ringP(PM_INV, prod), now, __fadd_rn(w, f));
+        emit(ringG(GM_INV), now, __fadd_rn(sc->tot_wip, sc->fgc_sum));
+    }
+    // _log_delivery_performance + _log_lead_time, factory_sim.py:606-654
+    __device__ __forceinline__ void delivery_records(int d, int prod, bool delivered) {
+        float q = ARR(float, do_qty)[d];
+        float due = ARR(float, do_due)[d];
+        if (!delivered || now == 0.0f) {          // `if not delivered` (also true for delivered == 0, quirk E6)
+            emit(ringP(PM_LOST, prod), now, q);
+        } else if (now <= due) {
+            emit(ringP(PM_ONTIME, prod), now, q);
+            emit(ringP(PM_EARLY, prod), now, __fsub_rn(due, now));
+        } else {
+            emit(ringP(PM_LATE, prod), now, q);
+            emit(ringP(PM_TARDY, prod), now, __fsub_rn(now, due));
+        }
+        emit(ringP(PM_LEAD, prod), now, __fsub_rn(now, ARR(float, do_arr)[d]));
+    }
+    // resource `queue` records, factory_sim.py:227-242 / 343-358
+    __device__ __forceinline__ void queue_log_add(int r, float q) {
+        float last = ARR(float, r_lastq)[r];
+        float val;
+        if (isnan(last)) {
+            val = ARR(float, r_qq)[r];
+        } else {
+            val = __fadd_rn(last, q);
+            ARR(float, r_qq)[r] = val;
+        }
+        emit(ringR(RM_QUEUE, r), now, val);
+        ARR(float, r_lastq)[r] = val;
+    }
+
+    // ------------------------------------------------------------------ pools and stores
+    __device__ __forceinline__ uint32_t alloc_po() {
+        uint32_t i = sc->po_free;
+        if (i == kNone) { status = MSIM_ST_PO_POOL_OVERFLOW; return 0; }
+        sc->po_free = ARR(uint8_t, po_next)[i];
+        return i;
+    }
+    __device__ __forceinline__ void free_po(uint32_t i) {
+        ARR(uint8_t, po_next)[i] = sc->po_free;
+        ARR(uint8_t, po_loc)[i] = LOC_NONE;
+        sc->po_free = (uint8_t)i;
+    }
+    __device__ __forceinline__ uint32_t alloc_do() {
+        uint32_t i = sc->do_free;
+        if (i == kNone) { status = MSIM_ST_DO_POOL_OVERFLOW; return 0; }
+        sc->do_free = ARR(uint8_t, do_next)[i];
+        return i;
+    }
+    __device__ __forceinline__ void free_do(uint32_t i) {
+        ARR(uint8_t, do_next)[i] = sc->do_free;
+        sc->do_free = (uint8_t)i;
+    }
+    // generic singly linked FIFO through a `next` byte array
+    __device__ __forceinline__ void list_append(uint8_t* head, uint8_t* tail, uint8_t* next, uint32_t i) {
+        next[i] = kNone;
+        uint32_t t = *tail;
+        if (t == kNone) *head = (uint8_t)i; else next[t] = (uint8_t)i;
+        *tail = (uint8_t)i;
+    }
+    __device__ __forceinline__ uint32_t list_pop(uint8_t* head, uint8_t* tail, const uint8_t* next) {
+        uint32_t h = *head;
+        uint32_t n = next[h];
+        *head = (uint8_t)n;
+        if (n == kNone) *tail = kNone;
+        return h;
+    }
+
+    // Container._trigger_get on finished_goods[prod]: serve blocked getters from the head, stop at the first
+    // one that cannot be satisfied (SimPy Container._do_get returns None => head-of-line blocking)
+    __device__ __forceinline__ void serve_fg(int prod) {
+        uint32_t h = ARR(uint8_t, p_fgqh)[prod];
+        if (h == kNone) return;
+        float lvl = ARR(float, p_fg)[prod];
+        const uint8_t* nx = ARR(uint8_t, do_next);
+        while (h != kNone) {
+            float q = ARR(float, do_qty)[h];
+            if (!(lvl >= q)) break;
+            lvl = __fsub_rn(lvl, q);
+            pushN(EV(OP_SHIP_GOT, prod, h));
+            h = nx[h];
+        }
+        ARR(float, p_fg)[prod] = lvl;
+        ARR(uint8_t, p_fgqh)[prod] = (uint8_t)h;
+        if (h == kNone) ARR(uint8_t, p_fgqt)[prod] = kNone;
+    }
+    // finished_goods[prod].get(quantity) issued by a delivery process (ContainerGet.__init__)
+    __device__ __forceinline__ void fg_get(int d, int prod) {
+        if (!(ARR(float, do_qty)[d] > 0.0f)) { status = MSIM_ST_AMOUNT_NONPOSITIVE; return; }
+        list_append(ARR(uint8_t, p_fgqh) + prod, ARR(uint8_t, p_fgqt) + prod, ARR(uint8_t, do_next), d);
+        serve_fg(prod);
+    }
+    // FilterStore._trigger_get on resource_input[r] when a put event is processed
+    __device__ __forceinline__ void serve_mach(int r) {
+        if ((sc->mach_wait >> r) & 1u) {
+            if (ARR(uint8_t, r_inh)[r] != kNone) {
+                uint32_t po = list_pop(ARR(uint8_t, r_inh) + r, ARR(uint8_t, r_int) + r, ARR(uint8_t, po_next));
+                ARR(uint8_t, po_loc)[po] = LOC_NONE;
+                sc->mach_wait &= ~(1u << r);
+                pushN(EV(OP_MACH_GOT, r, po));
+            }
+        }
+    }
+    // _transportation loop top: resource_output[r].get()   factory_sim.py:298-302
+    __device__ __forceinline__ void trans_get(int r) {
+        if (ARR(uint8_t, r_outh)[r] != kNone) {
+            uint32_t po = list_pop(ARR(uint8_t, r_outh) + r, ARR(uint8_t, r_outt) + r, ARR(uint8_t, po_next));
+            ARR(uint8_t, po_loc)[po] = LOC_NONE;
+            pushN(EV(OP_TRANS_GOT, r, po));
+        } else {
+            sc->trans_wait |= 1u << r;
+        }
+    }
+    // scheduler loop top: inbound_demand_orders.get()      factory_sim.py:182
+    __device__ __forceinline__ void sched_get() {
+        if (sc->inb_head != kNone) {
+            uint32_t d = list_pop(&sc->inb_head, &sc->inb_tail, ARR(uint8_t, do_next));
+            pushN(EV(OP_SCHED_GOT, 0, d));
+        } else {
+            sc->sched_wait = 1;
+        }
+    }
+    // _delivery_orders loop top: outbound[prod].get()       factory_sim.py:469-471
+    __device__ __forceinline__ void deliv_get(int prod) {
+        if (ARR(uint8_t, p_obh)[prod] != kNone) {
+            uint32_t d = list_pop(ARR(uint8_t, p_obh) + prod, ARR(uint8_t, p_obt) + prod, ARR(uint8_t, do_next));
+            pushN(EV(OP_DELIV_GOT, prod, d));
+        } else {
+            sc->deliv_wait |= 1u << prod;
+        }
+    }
+    // _generate_demand_orders loop top: three draws then timeout(freq)   factory_sim.py:154-164
+    __device__ __forceinline__ void demand_draw(int prod) {
+        float gap = draw_scalar(0, TAB(DDist, t_freq)[prod]);
+        float q = rintf(draw_scalar(0, TAB(DDist, t_qty)[prod]));     // round(x, 0): ties to even
+        float due = draw_scalar(0, TAB(DDist, t_due)[prod]);
+        ARR(float, p_dqty)[prod] = q;
+        ARR(float, p_ddue)[prod] = due;
+        timer(p.lay.R + prod, __fadd_rn(now, gap), EV(OP_TO_DEMAND, prod, 0));
+    }
+    // order_selection: policy is a compile-time device function
+    __device__ __forceinline__ void mach_select(int r) {
+        uint32_t h = ARR(uint8_t, r_inh)[r];
+        if (h == kNone) { sc->mach_wait |= 1u << r; return; }   // plain get() on an empty queue
+        uint32_t pick = h;
+        if (POLICY == MSIM_POLICY_MAX_PRIORITY) {
+            // max(orders, key=priority): first maximum in queue order (simple_scheduler/simulation.py:36)
+            const uint8_t* nx = ARR(uint8_t, po_next);
+            const float* pr = ARR(float, po_prio);
+            float best = pr[h];
+            uint32_t prev = kNone, pick_prev = kNone;
+            for (uint32_t i = h; i != kNone; prev = i, i = nx[i]) {
+                if (pr[i] > best) { best = pr[i]; pick = i; pick_prev = prev; }
+            }
+            if (pick != h) {      // unlink from the middle
+                uint8_t* nxw = ARR(uint8_t, po_next);
+                nxw[pick_prev] = nxw[pick];
+                if (nxw[pick] == kNone) ARR(uint8_t, r_int)[r] = (uint8_t)pick_prev;
+            } else {
+                list_pop(ARR(uint8_t, r_inh) + r, ARR(uint8_t, r_int) + r, ARR(uint8_t, po_next));
+            }
+        } else {
+            list_pop(ARR(uint8_t, r_inh) + r, ARR(uint8_t, r_int) + r, ARR(uint8_t, po_next));
+        }
+        ARR(uint8_t, po_loc)[pick] = LOC_NONE;
+        pushN(EV(OP_MACH_GOT, r, pick));
+    }
+    // _production_system loop top   factory_sim.py:375-380
+    __device__ __forceinline__ void mach_loop_top(int r) {
+        if (ARR(float, r_utf)[r] >= ARR(float, r_tbf)[r]) {
+            ARR(float, r_start)[r] = now;                                  // breakdown_start, :272
+            float ttr = draw_scalar(3, TAB(DDist, t_ttr)[r]);              // :275
+            ARR(uint8_t, r_phase)[r] = PH_TTR;
+            timer(r, __fadd_rn(now, ttr), EV(OP_TO_TTR, r, 0));
+            return;
+        }
+        mach_select(r);
+    }
+
+    // ------------------------------------------------------------------ one micro-event
+    __device__ __forceinline__ void dispatch(uint32_t ev) {
+        const uint32_t op = ev & 0xFFu;
+        const int a = (ev >> 8) & 0xFF;
+        const int b = (ev >> 16) & 0xFF;
+        nev++;
+        switch (op) {
+        case OP_TO_WARMUP:                                       // factory_sim.py:97-99
+            warm = 1;
+            nev++;                                               // process-end event
+            break;
+        case OP_TO_DEMAND: {                                     // :166-175
+            uint32_t d = alloc_do();
+            if (status) break;
+            ARR(uint8_t, do_prod)[d] = (uint8_t)a;
+            ARR(float, do_qty)[d] = ARR(float, p_dqty)[a];
+            ARR(float, do_due)[d] = __fadd_rn(ARR(float, p_ddue)[a], now);
+            ARR(float, do_arr)[d] = now;
+            list_append(&sc->inb_head, &sc->inb_tail, ARR(uint8_t, do_next), d);
+            pushN(EV(OP_PUT_INBOUND, a, 0));
+            break;
+        }
+        case OP_PUT_INBOUND:                                     // StorePut[inbound] processed
+            if (sc->sched_wait && sc->inb_head != kNone) {
+                uint32_t d = list_pop(&sc->inb_head, &sc->inb_tail, ARR(uint8_t, do_next));
+                sc->sched_wait = 0;
+                pushN(EV(OP_SCHED_GOT, 0, d));
+            }
+            demand_draw(a);
+            break;
+        case OP_SCHED_GOT: {                                     // scheduler :183-193
+            int prod = ARR(uint8_t, do_prod)[b];
+            uint32_t po = alloc_po();
+            if (status) break;
+            ARR(uint8_t, po_prod)[po] = (uint8_t)prod;
+            ARR(float, po_qty)[po] = ARR(float, do_qty)[b];
+            if (POLICY == MSIM_POLICY_MAX_PRIORITY) ARR(float, po_prio)[po] = 0.0f;
+            pushU(EV(OP_INIT_RELEASE, 0, po));
+            list_append(ARR(uint8_t, p_obh) + prod, ARR(uint8_t, p_obt) + prod, ARR(uint8_t, do_next), b);
+            pushN(EV(OP_PUT_OUTBOUND, prod, 0));
+            break;
+        }
+        case OP_PUT_OUTBOUND:                                    // StorePut[outbound[p]] processed
+            if (((sc->deliv_wait >> a) & 1u) && ARR(uint8_t, p_obh)[a] != kNone) {
+                uint32_t d = list_pop(ARR(uint8_t, p_obh) + a, ARR(uint8_t, p_obt) + a, ARR(uint8_t, do_next));
+                sc->deliv_wait &= ~(1u << a);
+                pushN(EV(OP_DELIV_GOT, a, d));
+            }
+            sched_get();
+            break;
+        case OP_INIT_RELEASE: {                                  // _release_order :195-211
+            int prod = ARR(uint8_t, po_prod)[b];
+            int first = TAB(uint8_t, t_step_res)[TAB(uint16_t, t_route_start)[prod]];
+            ARR(uint8_t, po_done)[b] = 0;
+            ARR(float, po_rel)[b] = now;
+            list_append(ARR(uint8_t, r_inh) + first, ARR(uint8_t, r_int) + first, ARR(uint8_t, po_next), b);
+            ARR(uint8_t, po_loc)[b] = LOC_IN;
+            pushN(EV(OP_REL_PUT1, first, b));
+            break;
+        }
+        case OP_REL_PUT1: {                                      // :211-212
+            serve_mach(a);
+            float q = ARR(float, po_qty)[b];
+            if (!(q > 0.0f)) { status = MSIM_ST_AMOUNT_NONPOSITIVE; break; }
+            int prod = ARR(uint8_t, po_prod)[b];
+            ARR(float, p_wip)[prod] = __fadd_rn(ARR(float, p_wip)[prod], q);
+            pushN(EV(OP_REL_PUT2, a, b));
+            break;
+        }
+        case OP_REL_PUT2: {                                      // :214-242
+            float q = ARR(float, po_qty)[b];
+            int prod = ARR(uint8_t, po_prod)[b];
+            sc->tot_wip = __fadd_rn(sc->tot_wip, q);
+            ARR(float, r_qq)[a] = __fadd_rn(ARR(float, r_qq)[a], q);
+            if (warm) {
+                emit(ringP(PM_RELEASED, prod), now, q);
+                inventory(prod, true, false);
+                if (p.log_queues) queue_log_add(a, q);
+            }
+            nev++;                                               // process-end event
+            break;
+        }
+        case OP_MACH_GOT: {                                      // _production_system :380-395
+            float q = ARR(float, po_qty)[b];
+            ARR(float, r_qq)[a] = __fsub_rn(ARR(float, r_qq)[a], q);
+            if (warm && p.log_queues) {
+                emit(ringR(RM_QUEUE, a), now, ARR(float, r_qq)[a]);
+                ARR(float, r_lastq)[a] = ARR(float, r_qq)[a];
+            }
+            ARR(uint8_t, r_cur)[a] = (uint8_t)b;
+            ARR(uint8_t, po_loc)[b] = LOC_PROC;
+            pushN(EV(OP_MACH_PUTPROC, a, 0));
+            break;
+        }
+        case OP_MACH_PUTPROC: {                                  // :397-421 (setup drawn on every operation, quirk E1)
+            float setup = draw_scalar(1, TAB(DDist, t_setup)[a]);
+            ARR(float, r_setup)[a] = setup;
+            if (warm) emit(ringR(RM_SETUP, a), now, setup);
+            pushN(EV(OP_MACH_REQ, a, 0));
+            break;
+        }
+        case OP_MACH_REQ:                                        // :423
+            ARR(uint8_t, r_phase)[a] = PH_SETUP;
+            timer(a, __fadd_rn(now, ARR(float, r_setup)[a]), EV(OP_TO_SETUP, a, 0));
+            break;
+        case OP_TO_SETUP: {                                      // :425-440
+            uint32_t po = ARR(uint8_t, r_cur)[a];
+            int prod = ARR(uint8_t, po_prod)[po];
+            int step = TAB(uint16_t, t_route_start)[prod] + ARR(uint8_t, po_done)[po];
+            ARR(float, r_start)[a] = now;
+            double total = draw_batch(TAB(DDist, t_step_dist)[step], (int)ARR(float, po_qty)[po]);
+            if (total < 0.0) { status = MSIM_ST_NEGATIVE_DELAY; break; }
+            ARR(uint8_t, r_phase)[a] = PH_PROC;
+            timer(a, __fadd_rn(now, __double2float_rn(total)), EV(OP_TO_PROC, a, 0));
+            break;
+        }
+        case OP_TO_PROC: {                                       // :442-451
+            uint32_t po = ARR(uint8_t, r_cur)[a];
+            float busy = round6(__fsub_rn(now, ARR(float, r_start)[a]));
+            ARR(float, r_busy)[a] = busy;
+            ARR(float, r_utf)[a] = __fadd_rn(ARR(float, r_utf)[a], busy);
+            ARR(uint8_t, po_done)[po]++;
+            ARR(uint8_t, po_loc)[po] = LOC_NONE;
+            pushN(EV(OP_MACH_GOTPROC, a, 0));
+            break;
+        }
+        case OP_MACH_GOTPROC: {                                  // :452
+            uint32_t po = ARR(uint8_t, r_cur)[a];
+            list_append(ARR(uint8_t, r_outh) + a, ARR(uint8_t, r_outt) + a, ARR(uint8_t, po_next), po);
+            ARR(uint8_t, po_loc)[po] = LOC_OUT;
+            pushN(EV(OP_MACH_PUTOUT, a, 0));
+            break;
+        }
+        case OP_MACH_PUTOUT:                                     // :452-461, then loop top :375-380
+            if (((sc->trans_wait >> a) & 1u) && ARR(uint8_t, r_outh)[a] != kNone) {
+                uint32_t po = list_pop(ARR(uint8_t, r_outh) + a, ARR(uint8_t, r_outt) + a, ARR(uint8_t, po_next));
+                ARR(uint8_t, po_loc)[po] = LOC_NONE;
+                sc->trans_wait &= ~(1u << a);
+                pushN(EV(OP_TRANS_GOT, a, po));
+            }
+            if (warm) emit(ringR(RM_UTIL, a), now, ARR(float, r_busy)[a]);
+            nev++;                                               // Release event of the `with` block
+            mach_loop_top(a);
+            break;
+        case OP_TO_TTR:                                          // _breakdowns :277-289
+            if (warm) emit(ringR(RM_BREAKDOWN, a), ARR(float, r_start)[a], round6(__fsub_rn(now, ARR(float, r_start)[a])));
+            ARR(float, r_tbf)[a] = draw_scalar(3, TAB(DDist, t_tbf)[a]);
+            ARR(float, r_utf)[a] = 0.0f;
+            mach_select(a);
+            break;
+        case OP_TRANS_GOT:                                       // _transportation :300-304
+            ARR(uint8_t, r_tcur)[a] = (uint8_t)b;
+            ARR(uint8_t, po_loc)[b] = LOC_TRANS;
+            pushN(EV(OP_TRANS_PUT, a, 0));
+            break;
+        case OP_TRANS_PUT: {                                     // :306-310 / :329-335
+            uint32_t po = ARR(uint8_t, r_tcur)[a];
+            int prod = ARR(uint8_t, po_prod)[po];
+            int total = TAB(uint16_t, t_route_start)[prod + 1] - TAB(uint16_t, t_route_start)[prod];
+            ARR(uint8_t, po_loc)[po] = LOC_NONE;
+            pushN(EV(ARR(uint8_t, po_done)[po] == total ? OP_TRANS_GOT2_FINAL : OP_TRANS_GOT2_NEXT, a, 0));
+            break;
+        }
+        case OP_TRANS_GOT2_FINAL: {                              // :311
+            uint32_t po = ARR(uint8_t, r_tcur)[a];
+            int prod = ARR(uint8_t, po_prod)[po];
+            ARR(float, p_fg)[prod] = __fadd_rn(ARR(float, p_fg)[prod], ARR(float, po_qty)[po]);
+            pushN(EV(OP_TRANS_FGPUT, a, 0));
+            break;
+        }
+        case OP_TRANS_FGPUT: {                                   // ContainerPut[FG] processed, then :312
+            uint32_t po = ARR(uint8_t, r_tcur)[a];
+            int prod = ARR(uint8_t, po_prod)[po];
+            serve_fg(prod);
+            float q = ARR(float, po_qty)[po];
+            float w = ARR(float, p_wip)[prod];
+            if (w >= q) {
+                ARR(float, p_wip)[prod] = __fsub_rn(w, q);
+                pushN(EV(OP_TRANS_WIPGET, a, 0));
+            } else {
+                status = MSIM_ST_WIP_GET_BLOCKED;
+            }
+            break;
+        }
+        case OP_TRANS_WIPGET: {                                  // :314-326
+            uint32_t po = ARR(uint8_t, r_tcur)[a];
+            int prod = ARR(uint8_t, po_prod)[po];
+            sc->tot_wip = __fsub_rn(sc->tot_wip, ARR(float, po_qty)[po]);
+            float f = ARR(float, p_fg)[prod];
+            float old = ARR(float, p_fgc)[prod];
+            ARR(float, p_fgc)[prod] = f;
+            sc->fgc_sum = __fadd_rn(sc->fgc_sum, __fsub_rn(f, old));
+            if (warm) {
+                emit(ringP(PM_FLOW, prod), now, __fsub_rn(now, ARR(float, po_rel)[po]));
+                inventory(prod, true, true);
+            }
+            free_po(po);
+            trans_get(a);
+            break;
+        }
+        case OP_TRANS_GOT2_NEXT: {                               // :330-336
+            uint32_t po = ARR(uint8_t, r_tcur)[a];
+            int prod = ARR(uint8_t, po_prod)[po];
+            int nxt = TAB(uint8_t, t_step_res)[TAB(uint16_t, t_route_start)[prod] + ARR(uint8_t, po_done)[po]];
+            list_append(ARR(uint8_t, r_inh) + nxt, ARR(uint8_t, r_int) + nxt, ARR(uint8_t, po_next), po);
+            ARR(uint8_t, po_loc)[po] = LOC_IN;
+            pushN(EV(OP_TRANS_PUTIN, a, nxt));
+            break;
+        }
+        case OP_TRANS_PUTIN: {                                   // :336-358
+            serve_mach(b);
+            float q = ARR(float, po_qty)[ARR(uint8_t, r_tcur)[a]];
+            ARR(float, r_qq)[b] = __fadd_rn(ARR(float, r_qq)[b], q);
+            if (warm && p.log_queues) queue_log_add(b, q);
+            trans_get(a);
+            break;
+        }
+        case OP_DELIV_GOT:                                       // _delivery_orders :469-480
+            pushU(EV(OP_INIT_SHIP, a, b));
+            deliv_get(a);
+            break;
+        case OP_INIT_SHIP:                                       // :482-549 (onDue with patch P1)
+            if (p.delivery_mode == MSIM_DELIVERY_AS_READY) {
+                fg_get(b, a);
+            } else if (p.delivery_mode == MSIM_DELIVERY_INSTANTLY) {
+                if (ARR(float, p_fg)[a] >= ARR(float, do_qty)[b]) {
+                    fg_get(b, a);
+                } else {
+                    if (warm) {
+                        inventory(a, false, true);
+                        delivery_records(b, a, false);
+                    }
+                    nev++;                                       // process-end event
+                    free_do(b);
+                }
+            } else {
+                float wait = __fsub_rn(ARR(float, do_due)[b], now);
+                if (wait > 0.0f) {
+                    float t = __fadd_rn(now, wait);
+                    if (t == now) {
+                        pushN(EV(OP_TO_SHIP, a, b));
+                    } else {
+                        ARR(float, do_tt)[b] = t;
+                        ARR(uint32_t, do_eid)[b] = tseq++;
+                    }
+                } else {
+                    fg_get(b, a);
+                }
+            }
+            break;
+        case OP_TO_SHIP:
+            fg_get(b, a);
+            break;
+        case OP_SHIP_GOT:                                        // ContainerGet[FG] processed
+            if (warm) {
+                inventory(a, false, true);
+                delivery_records(b, a, true);
+            }
+            nev++;                                               // process-end event
+            free_do(b);
+            break;
+        default:
+            break;
+        }
+    }
+
+    // lane 0: run zero-delay events until the warp has to cooperate again
+    __device__ __forceinline__ int drain() {
+        for (;;) {
+            uint32_t ev;
+            if (pending) {
+                ev = pending;
+                pending = 0;
+            } else if (uqh != uqt) {
+                ev = ARR(uint32_t, uq)[uqh & (uint32_t)(p.lay.UQ - 1)];
+                uqh++;
+            } else if (same_left) {
+                return REQ_ADVANCE;          // calendar entries at `now` precede NORMAL events created at `now`
+            } else if (nqh != nqt) {
+                ev = ARR(uint32_t, nq)[nqh & (uint32_t)(p.lay.NQ - 1)];
+                nqh++;
+            } else {
+                return REQ_ADVANCE;
+            }
+            dispatch(ev);
+            if (status) return REQ_DONE;
+            if (nstage >= (uint32_t)kStageFlushAt) return REQ_FLUSH;
+        }
+    }
+
+    // t = 0: construction order of FactorySimulation._initiate_environment (factory_sim.py:61-89) -- the Initialize
+    // events are URGENT and already ordered by eid, so they are executed directly in that order.
+    __device__ __forceinline__ void boot() {
+        const int R = p.lay.R, P = p.lay.P;
+        now = 0.0f; warm = 0; nqh = nqt = uqh = uqt = 0; nstage = 0; logc = 0; nev = 0; tseq = 0; same_left = 0;
+        status = 0; pending = 0;
+        for (int r = 0; r < R; ++r) {                            // _start_resources :248-261 (draws at construction)
+            const DDist& tb_ = TAB(DDist, t_tbf)[r];
+            ARR(float, r_tbf)[r] = tb_.kind == MSIM_DIST_NONE ? CUDART_INF_F : draw_scalar(3, tb_);
+        }
+        nev++;                                                   // Initialize[warmup]
+        timer(R + P, p.warmup, EV(OP_TO_WARMUP, 0, 0));
+        for (int r = 0; r < R; ++r) {
+            nev += 2;                                            // Initialize[_transportation], Initialize[_production_system]
+            sc->trans_wait |= 1u << r;
+            mach_loop_top(r);
+        }
+        for (int prod = 0; prod < P; ++prod) {
+            nev += 2;                                            // Initialize[_generate_demand_orders], Initialize[_delivery_orders]
+            demand_draw(prod);
+            sc->deliv_wait |= 1u << prod;
+        }
+        nev++;                                                   // Initialize[scheduler]
+        sc->sched_wait = 1;
+    }
+#undef ARR
+#undef TAB
+};
+
+// cooperative log flush: one 128-bit record per lane (st.global.v4, 512 contiguous bytes per warp) into the
+// replication's HBM ring + fused per-ring reductions.  Lanes holding records of the same ring are grouped with
+// match.any; the group leader adds the group's values in lane (= emission) order, so the float64 sums are
+// deterministic and independent of how replications are sharded.
+__device__ __forceinline__ void warp_flush(const KParams& p, const unsigned char* sb, long long rep, int lane, uint32_t n,
+                                           uint32_t base) {
+    const Lay& L = p.lay;
+    uint4 rec = make_uint4(0u, 0u, 0xFFFFFFFFu, 0u);
+    if ((uint32_t)lane < n) rec = reinterpret_cast<const uint4*>(sb + L.stage)[lane];
+    if ((uint32_t)lane < n && p.a.log != nullptr && rep < p.a.n_log_reps) {
+        unsigned long long at = ((unsigned long long)base + (unsigned)lane) % (unsigned long long)p.a.log_cap;
+        reinterpret_cast<uint4*>(p.a.log)[rep * p.a.log_cap + (long long)at] = rec;
+    }
+    unsigned grp = __match_any_sync(FULLMASK, rec.z);
+    bool leader = ((uint32_t)lane < n) && (lane == __ffs(grp) - 1);
+    double tot = 0.0;
+    float v = __uint_as_float(rec.y);
+    for (uint32_t j = 0; j < n; ++j) {
+        float vj = __shfl_sync(FULLMASK, v, (int)j);
+        if ((grp >> j) & 1u) tot += (double)vj;
+    }
+    if (leader) {
+        p.a.acc_sum[rep * L.K + rec.z] += tot;
+        p.a.acc_cnt[rep * L.K + rec.z] += (uint32_t)__popc(grp);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+template <int POLICY, int RNG>
+__global__ void __launch_bounds__(256) sim_kernel(const __grid_constant__ KParams p) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    const Lay& L = p.lay;
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    // block-shared scenario tables
+    for (int i = threadIdx.x; i < L.t_bytes / 4; i += blockDim.x)
+        reinterpret_cast<uint32_t*>(smem)[i] = reinterpret_cast<const uint32_t*>(p.tables)[i];
+    __syncthreads();
+    unsigned char* sb = smem + L.t_bytes + (size_t)warp * L.slab_bytes;
+    Sim<POLICY, RNG> s(p, sb, smem);
+    Scal* sc = s.sc;
+    const bool on_due = p.delivery_mode == MSIM_DELIVERY_ON_DUE;
+    const uint32_t until_bits = __float_as_uint(p.run_until);
+
+    for (;;) {
+        long long rep = 0;
+        if (lane == 0) rep = (long long)atomicAdd(p.work_counter, 1ull);
+        rep = __shfl_sync(FULLMASK, rep, 0);
+        if (rep >= p.a.n_reps) break;
+        s.rep = rep;
+
+        // ---- cooperative slab initialisation
+        for (int i = lane; i < L.slab_bytes / 4; i += 32) reinterpret_cast<uint32_t*>(sb)[i] = 0u;
+        __syncwarp();
+        for (int i = lane; i < L.NT; i += 32) reinterpret_cast<float*>(sb + L.tm_time)[i] = CUDART_INF_F;
+        for (int i = lane; i < L.MD; i += 32) {
+            reinterpret_cast<float*>(sb + L.do_tt)[i] = CUDART_INF_F;
+            (sb + L.do_next)[i] = (uint8_t)(i + 1 < L.MD ? i + 1 : kNone);
+        }
+        for (int i = lane; i < L.MP; i += 32) (sb + L.po_next)[i] = (uint8_t)(i + 1 < L.MP ? i + 1 : kNone);
+        for (int i = lane; i < L.R; i += 32) {
+            (sb + L.r_inh)[i] = kNone; (sb + L.r_int)[i] = kNone; (sb + L.r_outh)[i] = kNone; (sb + L.r_outt)[i] = kNone;
+            reinterpret_cast<float*>(sb + L.r_lastq)[i] = CUDART_NAN_F;
+        }
+        for (int i = lane; i < L.P; i += 32) {
+            (sb + L.p_obh)[i] = kNone; (sb + L.p_obt)[i] = kNone; (sb + L.p_fgqh)[i] = kNone; (sb + L.p_fgqt)[i] = kNone;
+        }
+        for (int i = lane; i < L.K; i += 32) {
+            p.a.acc_sum[rep * L.K + i] = 0.0;
+            p.a.acc_cnt[rep * L.K + i] = 0u;
+        }
+        if (lane == 0) {
+            sc->inb_head = kNone; sc->inb_tail = kNone; sc->po_free = 0; sc->do_free = 0;
+            sc->fin_head = kNone; sc->fin_tail = kNone;
+            if (RNG == MSIM_RNG_REPLAY) {
+                long long oa = p.a.tape_A_off[rep], ob = p.a.tape_B_off[rep], oc = p.a.tape_C_off[rep], od = p.a.tape_D_off[rep];
+                sc->tbase[0] = p.a.tape_A + oa; sc->tlen[0] = (uint32_t)(p.a.tape_A_off[rep + 1] - oa);
+                sc->tbase[1] = p.a.tape_B + ob; sc->tlen[1] = (uint32_t)(p.a.tape_B_off[rep + 1] - ob);
+                sc->tbase[2] = p.a.tape_C + oc; sc->tlen[2] = (uint32_t)(p.a.tape_C_off[rep + 1] - oc);
+                sc->tbase[3] = p.a.tape_D + od; sc->tlen[3] = (uint32_t)(p.a.tape_D_off[rep + 1] - od);
+            } else {
+                uint64_t key = p.a.rep_seeds ? p.a.rep_seeds[rep] : rep_key(p.a.philox_seed, (uint64_t)(p.a.rep_offset + rep));
+                sc->k0 = (uint32_t)key; sc->k1 = (uint32_t)(key >> 32);
+            }
+        }
+        __syncwarp();
+        if (lane == 0) s.boot();
+        __syncwarp();
+
+        // ---- event loop
+        for (;;) {
+            int req = REQ_ADVANCE;
+            if (lane == 0) req = s.drain();
+            req = __shfl_sync(FULLMASK, req, 0);
+            uint32_t n = __shfl_sync(FULLMASK, s.nstage, 0);
+            if (req == REQ_FLUSH) {
+                warp_flush(p, sb, rep, lane, n, __shfl_sync(FULLMASK, s.logc, 0));
+                if (lane == 0) { s.logc += n; s.nstage = 0; }
+                __syncwarp();
+                continue;
+            }
+            if (req == REQ_DONE) break;
+
+            // ---- cooperative next-event selection: min over (time, eid) of every calendar slot
+            unsigned long long best = ~0ull;
+            int slot = -1, cnt = 0;
+            {
+                const float* tt = reinterpret_cast<const float*>(sb + L.tm_time);
+                const uint32_t* te = reinterpret_cast<const uint32_t*>(sb + L.tm_eid);
+                for (int i = lane; i < L.NT; i += 32) {
+                    unsigned long long k = ((unsigned long long)__float_as_uint(tt[i]) << 32) | te[i];
+                    uint32_t kt = (uint32_t)(k >> 32), bt = (uint32_t)(best >> 32);
+                    if (kt == bt) cnt++; else if (kt < bt) cnt = 1;
+                    if (k < best) { best = k; slot = i; }
+                }
+                if (on_due) {
+                    const float* dt = reinterpret_cast<const float*>(sb + L.do_tt);
+                    const uint32_t* de = reinterpret_cast<const uint32_t*>(sb + L.do_eid);
+                    for (int i = lane; i < L.MD; i += 32) {
+                        unsigned long long k = ((unsigned long long)__float_as_uint(dt[i]) << 32) | de[i];
+                        uint32_t kt = (uint32_t)(k >> 32), bt = (uint32_t)(best >> 32);
+                        if (kt == bt) cnt++; else if (kt < bt) cnt = 1;
+                        if (k < best) { best = k; slot = L.NT + i; }
+                    }
+                }
+            }
+#pragma unroll
+            for (int off = 16; off > 0; off >>= 1) {
+                unsigned long long ob = __shfl_xor_sync(FULLMASK, best, off);
+                int oc = __shfl_xor_sync(FULLMASK, cnt, off);
+                int os = __shfl_xor_sync(FULLMASK, slot, off);
+                uint32_t ot = (uint32_t)(ob >> 32), bt = (uint32_t)(best >> 32);
+                if (ot == bt) cnt += oc; else if (ot < bt) cnt = oc;
+                if (ob < best) { best = ob; slot = os; }
+            }
+            const uint32_t tbits = (uint32_t)(best >> 32);
+            if (tbits >= until_bits) break;      // the URGENT stop event at run_until precedes everything at that time
+            if (lane == 0) {
+                if (s.same_left == 0) {
+                    s.now = __uint_as_float(tbits);
+                    s.same_left = (uint32_t)cnt - 1u;
+                } else {
+                    s.same_left--;
+                }
+                sc->n_timeouts++;
+                uint32_t ev;
+                if (slot < L.R) {
+                    uint8_t ph = (sb + L.r_phase)[slot];
+                    ev = EV(ph == PH_SETUP ? OP_TO_SETUP : (ph == PH_PROC ? OP_TO_PROC : OP_TO_TTR), slot, 0);
+                    reinterpret_cast<float*>(sb + L.tm_time)[slot] = CUDART_INF_F;
+                } else if (slot < L.R + L.P) {
+                    ev = EV(OP_TO_DEMAND, slot - L.R, 0);
+                    reinterpret_cast<float*>(sb + L.tm_time)[slot] = CUDART_INF_F;
+                } else if (slot < L.NT) {
+                    ev = EV(OP_TO_WARMUP, 0, 0);
+                    reinterpret_cast<float*>(sb + L.tm_time)[slot] = CUDART_INF_F;
+                } else {
+                    int d = slot - L.NT;
+                    ev = EV(OP_TO_SHIP, (sb + L.do_prod)[d], d);
+                    reinterpret_cast<float*>(sb + L.do_tt)[d] = CUDART_INF_F;
+                }
+                s.pending = ev;
+            }
+            __syncwarp();
+        }
+
+        // ---- final flush + per-replication outputs
+        {
+            uint32_t n = __shfl_sync(FULLMASK, s.nstage, 0);
+            if (n > 0) {
+                warp_flush(p, sb, rep, lane, n, __shfl_sync(FULLMASK, s.logc, 0));
+                if (lane == 0) { s.logc += n; s.nstage = 0; }
+                __syncwarp();
+            }
+        }
+        if (lane == 0) {
+            p.a.n_events[rep] = (unsigned long long)s.nev + 1ull;     // + the stop event of run(until)
+            p.a.status[rep] = s.status;
+            if (p.a.n_timeouts) p.a.n_timeouts[rep] = sc->n_timeouts;
+            if (p.a.log_count && rep < p.a.n_log_reps) p.a.log_count[rep] = s.logc;
+            if (RNG == MSIM_RNG_PHILOX && p.a.rec_count) {
+                for (int k = 0; k < 4; ++k) p.a.rec_count[rep * 4 + k] = sc->draw[k];
+            }
+        }
+        __syncwarp();
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// per-ring experiment statistics: x = per-replication metric value; out[ring] += {sum x, sum x^2, n}
+__global__ void reduce_kernel(const double* __restrict__ acc_sum, const uint32_t* __restrict__ acc_cnt,
+                              const int32_t* __restrict__ status, long long n_reps, int K, int P, int R, double span,
+                              double* __restrict__ out) {
+    const int ring = blockIdx.x;
+    // metric class: 0 = sum, 1 = sum / span, 2 = mean  (metrics.py:43-67, factory_sim.py:758-763)
+    int cls;
+    if (ring < 3 * P) cls = 0;
+    else if (ring < 11 * P) cls = 2;
+    else if (ring < 11 * P + 3 * R) cls = 1;
+    else cls = 2;
+    double s1 = 0.0, s2 = 0.0, nn = 0.0;
+    for (long long i = threadIdx.x; i < n_reps; i += blockDim.x) {
+        if (status[i] != 0) continue;
+        double s = acc_sum[i * K + ring];
+        uint32_t c = acc_cnt[i * K + ring];
+        double x;
+        if (cls == 0) x = s;
+        else if (cls == 1) x = s / span;
+        else { if (c == 0) continue; x = s / (double)c; }
+        s1 += x; s2 += x * x; nn += 1.0;
+    }
+    __shared__ double sh[3][32];
+    for (int off = 16; off > 0; off >>= 1) {
+        s1 += __shfl_xor_sync(FULLMASK, s1, off);
+        s2 += __shfl_xor_sync(FULLMASK, s2, off);
+        nn += __shfl_xor_sync(FULLMASK, nn, off);
+    }
+    int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+    if (l == 0) { sh[0][w] = s1; sh[1][w] = s2; sh[2][w] = nn; }
+    __syncthreads();
+    if (w == 0) {
+        int nw = blockDim.x >> 5;
+        s1 = l < nw ? sh[0][l] : 0.0; s2 = l < nw ? sh[1][l] : 0.0; nn = l < nw ? sh[2][l] : 0.0;
+        for (int off = 16; off > 0; off >>= 1) {
+            s1 += __shfl_xor_sync(FULLMASK, s1, off);
+            s2 += __shfl_xor_sync(FULLMASK, s2, off);
+            nn += __shfl_xor_sync(FULLMASK, nn, off);
+        }
+        if (l == 0) { out[ring * 3 + 0] += s1; out[ring * 3 + 1] += s2; out[ring * 3 + 2] += nn; }
+    }
+}
+
+__global__ void test_philox_kernel(const uint32_t* ctr, const uint32_t* key, uint32_t* out, long long n) {
+    long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint32_t o[4];
+    philox4x32_10(ctr[4 * i], ctr[4 * i + 1], ctr[4 * i + 2], ctr[4 * i + 3], key[2 * i], key[2 * i + 1], o);
+    for (int k = 0; k < 4; ++k) out[4 * i + k] = o[k];
+}
+
+__global__ void test_variates_kernel(DDist d, uint64_t seed, int stream_id, int batch_count, double* out, long long n) {
+    long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    PhiloxStream s{(uint32_t)seed, (uint32_t)(seed >> 32), (uint32_t)stream_id, (uint32_t)i};
+    out[i] = batch_count < 0 ? (double)draw_scalar_philox(s, d.kind, d.d0, d.d1)
+                             : draw_batch_philox(s, d.kind, d.d0, d.d1, d.raw0, batch_count);
+}
+
+// ---------------------------------------------------------------------------------------------------------
+typedef void (*sim_fn)(const KParams);
+static sim_fn pick(int policy, int rng) {
+    if (policy == MSIM_POLICY_FIFO) return rng == MSIM_RNG_REPLAY ? sim_kernel<MSIM_POLICY_FIFO, MSIM_RNG_REPLAY>
+                                                                  : sim_kernel<MSIM_POLICY_FIFO, MSIM_RNG_PHILOX>;
+    if (policy == MSIM_POLICY_MAX_PRIORITY)
+        return rng == MSIM_RNG_REPLAY ? sim_kernel<MSIM_POLICY_MAX_PRIORITY, MSIM_RNG_REPLAY>
+                                      : sim_kernel<MSIM_POLICY_MAX_PRIORITY, MSIM_RNG_PHILOX>;
+    return nullptr;
+}
+
+int sim_kernel_attrs(int policy, int rng_mode, size_t smem, int* regs, int block, int* blocks_per_sm) {
+    sim_fn f = pick(policy, rng_mode);
+    if (!f) return MSIM_E_UNSUPPORTED;
+    cudaFuncAttributes at;
+    if (cudaFuncGetAttributes(&at, f) != cudaSuccess) return MSIM_E_CUDA;
+    if (regs) *regs = at.numRegs;
+    if (cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return MSIM_E_CUDA;
+    if (blocks_per_sm) {
+        int nb = 0;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, f, block, smem) != cudaSuccess) return MSIM_E_CUDA;
+        *blocks_per_sm = nb;
+    }
+    return 0;
+}
+
+int launch_sim(const KParams& p, int policy, int rng_mode, int grid, int block, size_t smem, void* stream) {
+    sim_fn f = pick(policy, rng_mode);
+    if (!f) return MSIM_E_UNSUPPORTED;
+    f<<<grid, block, smem, (cudaStream_t)stream>>>(p);
+    return cudaGetLastError() == cudaSuccess ? 0 : MSIM_E_CUDA;
+}
+
+int launch_reduce(const double* acc_sum, const uint32_t* acc_cnt, const int32_t* status, int64_t n_reps, int K, int P,
+                  int R, double span, double* out, void* stream) {
+    reduce_kernel<<<K, 256, 0, (cudaStream_t)stream>>>(acc_sum, acc_cnt, status, n_reps, K, P, R, span, out);
+    return cudaGetLastError() == cudaSuccess ? 0 : MSIM_E_CUDA;
+}
+
+int launch_test_philox(const uint32_t* ctr, const uint32_t* key, uint32_t* out, int64_t n) {
+    test_philox_kernel<<<(unsigned)((n + 127) / 128), 128>>>(ctr, key, out, n);
+    return cudaGetLastError() == cudaSuccess ? 0 : MSIM_E_CUDA;
+}
+
+int launch_test_variates(DDist d, uint64_t seed, int stream_id, int batch_count, double* out, int64_t n) {
+    test_variates_kernel<<<(unsigned)((n + 127) / 128), 128>>>(d, seed, stream_id, batch_count, out, n);
+    return cudaGetLastError() == cudaSuccess ? 0 : MSIM_E_CUDA;
+}
+
+} // namespace msim

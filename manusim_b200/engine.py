@@ -1,0 +1,256 @@
+"""BatchEngine: Python host of the batched replication kernel (thin layer over the C ABI in include/msim.h).
+
+PyTorch is used only for device/pinned memory, streams and torch.distributed; all simulation work happens in
+libmsim.so.  No CPU fallback: constructing an engine without a CUDA device raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+from typing import Dict, List, Optional, Sequence
+
+import numpy as np
+
+from . import _lib
+from .compiler import ScenarioTables
+
+RNG_PHILOX, RNG_REPLAY = 0, 1
+
+STATUS_TEXT = {0: "ok", 1: "Negative delay (SimPy ValueError)", 2: "Container amount <= 0 (SimPy ValueError)",
+               3: "production-order pool overflow", 4: "demand-order pool overflow", 5: "event FIFO overflow",
+               6: "replay tape exhausted", 7: "WIP get blocked (unsupported)", 8: "not run"}
+
+
+def _dist_array(dists):
+    arr = (_lib.Dist * len(dists))()
+    for i, d in enumerate(dists):
+        arr[i].kind = d.kind
+        arr[i].raw0, arr[i].raw1, arr[i].d0, arr[i].d1 = d.raw0, d.raw1, d.d0, d.d1
+    return arr
+
+
+def pack_tapes(tapes: Sequence[Dict[str, np.ndarray]]):
+    """[{A,B,C,D}] per replication -> concatenated value arrays + int64 offsets (C-ABI replay layout)."""
+    out = {}
+    for k, dt in (("A", np.float32), ("B", np.float32), ("C", np.float64), ("D", np.float32)):
+        vals = [np.asarray(t[k], dtype=dt) for t in tapes]
+        off = np.zeros(len(tapes) + 1, dtype=np.int64)
+        off[1:] = np.cumsum([len(v) for v in vals])
+        out[k] = np.concatenate(vals) if vals and off[-1] > 0 else np.zeros(1, dtype=dt)
+        out[k + "_off"] = off
+    return out
+
+
+@dataclass
+class BatchResult:
+    acc_sum: "object"       # [n, K] float64
+    acc_cnt: "object"       # [n, K] uint32 (torch: int32 view)
+    n_events: "object"      # [n] SimPy-equivalent events
+    n_timeouts: "object"    # [n] logical events (calendar pops)
+    status: "object"        # [n]
+    log: Optional["object"] = None        # [n_log, log_cap, 4] int32 view of 128-bit records
+    log_count: Optional["object"] = None  # [n_log]
+    rec: Optional[dict] = None            # recorded tapes (Philox mode)
+    kernel_ms: Optional[float] = None
+
+
+class BatchEngine:
+    """Compiled scenario on one GPU."""
+
+    def __init__(self, tables: ScenarioTables, device: Optional[int] = None):
+        import torch
+
+        if not torch.cuda.is_available():
+            raise RuntimeError("manusim_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback")
+        self.torch = torch
+        self.lib = _lib.load()
+        self.device = torch.device("cuda", torch.cuda.current_device() if device is None else device)
+        self.tables = tables
+        t = tables
+        self._keep = []
+        ct = _lib.Tables()
+        ct.n_resources, ct.n_products, ct.n_steps = t.R, t.P, int(t.route_start[-1])
+        rs = np.ascontiguousarray(t.route_start, dtype=np.int32)
+        sr = np.ascontiguousarray(t.step_resource, dtype=np.int32)
+        sb = np.ascontiguousarray(t.shipping_buffer, dtype=np.float64)
+        self._keep += [rs, sr, sb]
+        ct.route_start = rs.ctypes.data_as(C.POINTER(C.c_int32))
+        ct.step_resource = sr.ctypes.data_as(C.POINTER(C.c_int32))
+        ct.prod_shipping_buffer = sb.ctypes.data_as(C.POINTER(C.c_double))
+        for name in ("step_time", "res_setup", "res_tbf", "res_ttr", "prod_freq", "prod_qty", "prod_due"):
+            arr = _dist_array(getattr(t, name))
+            self._keep.append(arr)
+            setattr(ct, name, arr)
+        ct.run_until, ct.warmup = float(t.run_until), float(t.warmup)
+        ct.run_until_is_int, ct.warmup_is_int = int(isinstance(t.run_until, int)), int(isinstance(t.warmup, int))
+        ct.delivery_mode, ct.policy, ct.log_queues = t.delivery_mode, t.policy, int(t.log_queues)
+        if t.dbr:
+            d = t.dbr
+            cpt = np.ascontiguousarray(d["ccr_pt"], dtype=np.float64)
+            self._keep.append(cpt)
+            ct.dbr_ccr, ct.dbr_repair = d["ccr"], int(d["repair"])
+            ct.dbr_interval_is_int = int(isinstance(d["interval"], int))
+            ct.dbr_interval, ct.dbr_cb_target = float(d["interval"]), d["cb_target"]
+            ct.dbr_release_limit, ct.dbr_ccr_limit = d["release_limit"], d["ccr_limit"]
+            ct.dbr_min_lot, ct.dbr_ccr_setup = d["min_lot"], d["ccr_setup"]
+            ct.dbr_ccr_pt = cpt.ctypes.data_as(C.POINTER(C.c_double))
+        ct.max_production_orders, ct.max_demand_orders = t.max_production_orders, t.max_demand_orders
+        ct.fifo_capacity = t.fifo_capacity
+        self.handle = C.c_void_p()
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.msim_create(C.byref(ct), C.byref(self.handle)))
+        info = _lib.Info()
+        _lib.check(self.lib.msim_query(self.handle, C.byref(info)))
+        self.info = {f[0]: getattr(info, f[0]) for f in _lib.Info._fields_}
+        self.K = info.n_rings
+
+    def close(self):
+        if getattr(self, "handle", None) and self.handle.value:
+            self.lib.msim_destroy(self.handle)
+            self.handle = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ------------------------------------------------------------------ device-buffer path
+    def run(self, n_reps: int, seed: int = 0, rep_offset: int = 0, tapes: Optional[Sequence[dict]] = None,
+            rep_seeds=None, n_log_reps: int = 0, log_cap: int = 0, record_tapes: int = 0, stream=None,
+            out: Optional[BatchResult] = None) -> BatchResult:
+        """Launch n_reps replications; inputs/outputs are device tensors; asynchronous on `stream`."""
+        torch = self.torch
+        dev = self.device
+        K = self.K
+        if out is None:
+            out = self.alloc(n_reps, n_log_reps, log_cap)
+        a = _lib.RunArgs()
+        a.n_reps, a.rep_offset, a.philox_seed = n_reps, rep_offset, seed & 0xFFFFFFFFFFFFFFFF
+        keep = []
+        if tapes is not None:
+            a.rng_mode = RNG_REPLAY
+            packed = tapes if isinstance(tapes, dict) else pack_tapes(tapes)
+            for k in ("A", "B", "C", "D"):
+                v = packed[k] if torch.is_tensor(packed[k]) else torch.from_numpy(packed[k]).to(dev)
+                o = packed[k + "_off"] if torch.is_tensor(packed[k + "_off"]) else torch.from_numpy(packed[k + "_off"]).to(dev)
+                keep += [v, o]
+                setattr(a, "tape_" + k, v.data_ptr())
+                setattr(a, f"tape_{k}_off", o.data_ptr())
+        else:
+            a.rng_mode = RNG_PHILOX
+            if rep_seeds is not None:
+                rs = rep_seeds if torch.is_tensor(rep_seeds) else torch.from_numpy(
+                    np.asarray(rep_seeds, dtype=np.uint64).view(np.int64)).to(dev)
+                keep.append(rs)
+                a.rep_seeds = rs.data_ptr()
+            if record_tapes > 0:
+                rec = {"A": torch.zeros((n_reps, record_tapes), dtype=torch.float32, device=dev),
+                       "B": torch.zeros((n_reps, record_tapes), dtype=torch.float32, device=dev),
+                       "C": torch.zeros((n_reps, record_tapes), dtype=torch.float64, device=dev),
+                       "D": torch.zeros((n_reps, record_tapes), dtype=torch.float32, device=dev),
+                       "count": torch.zeros((n_reps, 4), dtype=torch.int32, device=dev)}
+                a.rec_A, a.rec_B, a.rec_C, a.rec_D = (rec[k].data_ptr() for k in "ABCD")
+                a.rec_cap, a.rec_count = record_tapes, rec["count"].data_ptr()
+                out.rec = rec
+        a.acc_sum, a.acc_cnt = out.acc_sum.data_ptr(), out.acc_cnt.data_ptr()
+        a.n_events, a.n_timeouts, a.status = out.n_events.data_ptr(), out.n_timeouts.data_ptr(), out.status.data_ptr()
+        if out.log is not None:
+            a.log, a.log_count = out.log.data_ptr(), out.log_count.data_ptr()
+            a.log_cap, a.n_log_reps = out.log.shape[1], out.log.shape[0]
+        s = stream if stream is not None else torch.cuda.current_stream(dev)
+        a.stream = s.cuda_stream
+        with torch.cuda.device(dev):
+            _lib.check(self.lib.msim_run(self.handle, C.byref(a)))
+        out._keep = keep
+        return out
+
+    def alloc(self, n_reps: int, n_log_reps: int = 0, log_cap: int = 0) -> BatchResult:
+        torch = self.torch
+        dev = self.device
+        res = BatchResult(
+            acc_sum=torch.empty((n_reps, self.K), dtype=torch.float64, device=dev),
+            acc_cnt=torch.empty((n_reps, self.K), dtype=torch.int32, device=dev),
+            n_events=torch.empty((n_reps,), dtype=torch.int64, device=dev),
+            n_timeouts=torch.empty((n_reps,), dtype=torch.int32, device=dev),
+            status=torch.full((n_reps,), 8, dtype=torch.int32, device=dev))
+        if n_log_reps > 0 and log_cap > 0:
+            res.log = torch.empty((min(n_log_reps, n_reps), log_cap, 4), dtype=torch.int32, device=dev)
+            res.log_count = torch.zeros((min(n_log_reps, n_reps),), dtype=torch.int32, device=dev)
+        return res
+
+    def reduce(self, res: BatchResult, out=None, stream=None):
+        """Per-ring {sum x, sum x^2, n} over this shard's replications -> [K,3] float64 (accumulated into out)."""
+        torch = self.torch
+        if out is None:
+            out = torch.zeros((self.K, 3), dtype=torch.float64, device=self.device)
+        s = stream if stream is not None else torch.cuda.current_stream(self.device)
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.msim_reduce_metrics(self.handle, res.acc_sum.data_ptr(), res.acc_cnt.data_ptr(),
+                                                    res.status.data_ptr(), res.acc_sum.shape[0], out.data_ptr(),
+                                                    s.cuda_stream))
+        return out
+
+    # ------------------------------------------------------------------ host-buffer path (end to end)
+    def alloc_host(self, n_reps: int, n_log_reps: int = 0, log_cap: int = 0) -> BatchResult:
+        torch = self.torch
+        pin = dict(pin_memory=True)
+        res = BatchResult(
+            acc_sum=torch.empty((n_reps, self.K), dtype=torch.float64, **pin),
+            acc_cnt=torch.empty((n_reps, self.K), dtype=torch.int32, **pin),
+            n_events=torch.empty((n_reps,), dtype=torch.int64, **pin),
+            n_timeouts=torch.empty((n_reps,), dtype=torch.int32, **pin),
+            status=torch.empty((n_reps,), dtype=torch.int32, **pin))
+        if n_log_reps > 0 and log_cap > 0:
+            res.log = torch.empty((min(n_log_reps, n_reps), log_cap, 4), dtype=torch.int32, **pin)
+            res.log_count = torch.zeros((min(n_log_reps, n_reps),), dtype=torch.int32, **pin)
+        return res
+
+    def run_host(self, n_reps: int, seed: int = 0, rep_offset: int = 0, tapes=None, rep_seeds=None,
+                 out: Optional[BatchResult] = None, n_log_reps: int = 0, log_cap: int = 0) -> BatchResult:
+        """Host buffers in, host buffers out (H2D + kernel + D2H inside the call, synchronous)."""
+        torch = self.torch
+        if out is None:
+            out = self.alloc_host(n_reps, n_log_reps, log_cap)
+        a = _lib.HostArgs()
+        a.n_reps, a.rep_offset, a.philox_seed = n_reps, rep_offset, seed & 0xFFFFFFFFFFFFFFFF
+        keep = []
+        if tapes is not None:
+            a.rng_mode = RNG_REPLAY
+            packed = tapes if isinstance(tapes, dict) else pack_tapes(tapes)
+            for k in ("A", "B", "C", "D"):
+                v, o = packed[k], packed[k + "_off"]
+                keep += [v, o]
+                setattr(a, "tape_" + k, v.data_ptr() if torch.is_tensor(v) else v.ctypes.data)
+                setattr(a, f"tape_{k}_off", o.data_ptr() if torch.is_tensor(o) else o.ctypes.data)
+        else:
+            a.rng_mode = RNG_PHILOX
+            if rep_seeds is not None:
+                rs = rep_seeds if torch.is_tensor(rep_seeds) else np.ascontiguousarray(rep_seeds, dtype=np.uint64)
+                keep.append(rs)
+                a.rep_seeds = rs.data_ptr() if torch.is_tensor(rs) else rs.ctypes.data
+        a.acc_sum, a.acc_cnt = out.acc_sum.data_ptr(), out.acc_cnt.data_ptr()
+        a.n_events, a.n_timeouts, a.status = out.n_events.data_ptr(), out.n_timeouts.data_ptr(), out.status.data_ptr()
+        if out.log is not None:
+            a.log, a.log_count = out.log.data_ptr(), out.log_count.data_ptr()
+            a.log_cap, a.n_log_reps = out.log.shape[1], out.log.shape[0]
+        ms = C.c_double(0.0)
+        a.kernel_ms = C.pointer(ms)
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.msim_run_host(self.handle, C.byref(a)))
+        out.kernel_ms = ms.value
+        return out
+
+
+def decode_log(log_row: np.ndarray, count: int):
+    """[cap,4] int32 view of 128-bit records -> (ring u32, time f32, value f32, seq u32) in emission order."""
+    cap = log_row.shape[0]
+    raw = np.ascontiguousarray(log_row).view(np.uint32).reshape(cap, 4)
+    if count > cap:   # ring wrapped: oldest record sits right after the newest
+        start = count % cap
+        raw = np.concatenate([raw[start:], raw[:start]])
+        n = cap
+    else:
+        n = count
+    raw = raw[:n]
+    return (raw[:, 2].copy(), raw[:, 0].copy().view(np.float32), raw[:, 1].copy().view(np.float32), raw[:, 3].copy())

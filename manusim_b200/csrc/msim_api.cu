@@ -279,7 +279,7 @@ extern "C" int msim_run(msim_handle_t h, const msim_run_args_t* a) {
     long long grid = (long long)h->n_sms * h->blocks_per_sm[rng];
     if (grid > blocks_needed) grid = blocks_needed;
     int rc = launch_sim(kp, h->policy, rng, (int)grid, h->warps_per_block * 32, h->smem_bytes, st);
-    if (rc != 0) return fail(rc, std::string("kernel launch failed: ") + cudaGetErrorString(cudaGetLastError()));
+    if (rc != 0) return fail(rc, "simulation kernel launch failed (grid/block/shared-memory configuration)");
     return 0;
 }
 

@@ -918,7 +918,7 @@ int sim_kernel_attrs(int policy, int rng_mode, size_t smem, int* regs, int block
     if (cudaFuncGetAttributes(&at, f) != cudaSuccess) return MSIM_E_CUDA;
     if (regs) *regs = at.numRegs;
     if (cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return MSIM_E_CUDA;
-    if (blocks_per_sm) {
+    if (blocks_per_sm) {  // NB: launch_sim re-raises the attribute if another handle lowered it
         int nb = 0;
         if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, f, block, smem) != cudaSuccess) return MSIM_E_CUDA;
         *blocks_per_sm = nb;
@@ -929,6 +929,12 @@ int sim_kernel_attrs(int policy, int rng_mode, size_t smem, int* regs, int block
 int launch_sim(const KParams& p, int policy, int rng_mode, int grid, int block, size_t smem, void* stream) {
     sim_fn f = pick(policy, rng_mode);
     if (!f) return MSIM_E_UNSUPPORTED;
+    // the opt-in limit is per function, not per handle: several handles with different slab sizes share a kernel
+    static size_t smem_set[3][2] = {{0, 0}, {0, 0}, {0, 0}};
+    if (smem > smem_set[policy][rng_mode]) {
+        if (cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return MSIM_E_CUDA;
+        smem_set[policy][rng_mode] = smem;
+    }
     f<<<grid, block, smem, (cudaStream_t)stream>>>(p);
     return cudaGetLastError() == cudaSuccess ? 0 : MSIM_E_CUDA;
 }

@@ -26,10 +26,10 @@ struct msim_handle_s {
     KParams kp;                 // layout + scalar parameters (args filled per run)
     int policy;
     int n_sms;
-    int warps_per_block;
-    int blocks_per_sm[2];       // per rng mode
+    int warps_per_block[2];     // per rng mode (the Philox and replay kernels differ in register use)
+    int blocks_per_sm[2];
     int regs[2];
-    size_t smem_bytes;
+    size_t smem_bytes[2];
     unsigned char* d_tables;
     unsigned long long* d_counter;
     double span;                // run_until - warmup
@@ -194,30 +194,28 @@ extern "C" int msim_create(const msim_tables_t* t, msim_handle_t* out) {
         return fail(MSIM_E_CUDA, "no CUDA device: libmsim has no CPU fallback");
     }
     h->n_sms = prop.multiProcessorCount;
-    // warps per block: as many replications per SM as shared memory allows, in CTAs of <= 8 warps
-    const size_t smem_sm = prop.sharedMemPerMultiprocessor;            // 228 KB on B200
+    // warps per block: maximise resident replications (= warps) per SM.  Shared memory, the per-CTA copy of the
+    // tables and the register file all bound it, so ask the occupancy calculator for every CTA width.
     const size_t smem_blk_max = prop.sharedMemPerBlockOptin;           // 227 KB
-    int best_w = 1, best_total = 0;
-    for (int w = 1; w <= 8; ++w) {
-        size_t need = (size_t)L.t_bytes + (size_t)w * L.slab_bytes;
-        if (need > smem_blk_max) break;
-        int nblk = (int)(smem_sm / (need + 1024));                     // 1 KB per-CTA reservation
-        if (nblk < 1) continue;
-        int warps = nblk * w;
-        if (warps > 64) warps = 64;
-        if (warps > best_total || (warps == best_total && w > best_w)) { best_total = warps; best_w = w; }
-    }
-    if (best_total == 0) { delete h; return fail(MSIM_E_UNSUPPORTED, "scenario does not fit shared memory"); }
-    h->warps_per_block = best_w;
-    kp.warps_per_block = best_w;
-    h->smem_bytes = (size_t)L.t_bytes + (size_t)best_w * L.slab_bytes;
     for (int rng = 0; rng < 2; ++rng) {
-        int rc = sim_kernel_attrs(h->policy, rng, h->smem_bytes, &h->regs[rng], best_w * 32, &h->blocks_per_sm[rng]);
-        if (rc != 0) {
-            delete h;
-            return fail(rc, rc == MSIM_E_UNSUPPORTED ? "policy not available in this build" : "kernel attribute query failed");
+        int best_w = 0, best_total = 0, best_blocks = 0;
+        for (int w = 1; w <= 8; ++w) {
+            size_t need = (size_t)L.t_bytes + (size_t)w * L.slab_bytes;
+            if (need > smem_blk_max) break;
+            int nblk = 0, regs = 0;
+            int rc = sim_kernel_attrs(h->policy, rng, need, &regs, w * 32, &nblk);
+            if (rc != 0) {
+                delete h;
+                return fail(rc, rc == MSIM_E_UNSUPPORTED ? "policy not available in this build" : "kernel attribute query failed");
+            }
+            h->regs[rng] = regs;
+            int warps = nblk * w;
+            if (warps > best_total || (warps == best_total && w > best_w)) { best_total = warps; best_w = w; best_blocks = nblk; }
         }
-        if (h->blocks_per_sm[rng] < 1) { delete h; return fail(MSIM_E_UNSUPPORTED, "kernel cannot be resident"); }
+        if (best_total == 0) { delete h; return fail(MSIM_E_UNSUPPORTED, "scenario does not fit shared memory"); }
+        h->warps_per_block[rng] = best_w;
+        h->blocks_per_sm[rng] = best_blocks;
+        h->smem_bytes[rng] = (size_t)L.t_bytes + (size_t)best_w * L.slab_bytes;
     }
     if (cudaMalloc(&h->d_tables, blob.size()) != cudaSuccess || cudaMalloc(&h->d_counter, 8) != cudaSuccess) {
         delete h;
@@ -249,7 +247,7 @@ extern "C" int msim_query(msim_handle_t h, msim_info_t* info) {
     info->n_rings = L.K;
     info->smem_per_replication = L.slab_bytes;
     info->smem_tables = L.t_bytes;
-    info->warps_per_block = h->warps_per_block;
+    info->warps_per_block = h->warps_per_block[0];
     info->blocks_per_sm = h->blocks_per_sm[0];
     info->n_sms = h->n_sms;
     info->regs_per_thread = h->regs[0];
@@ -275,10 +273,12 @@ extern "C" int msim_run(msim_handle_t h, const msim_run_args_t* a) {
     cudaStream_t st = (cudaStream_t)a->stream;
     CU(cudaMemsetAsync(h->d_counter, 0, 8, st));
     const int rng = a->rng_mode;
-    long long blocks_needed = (a->n_reps + h->warps_per_block - 1) / h->warps_per_block;
+    const int wpb = h->warps_per_block[rng];
+    kp.warps_per_block = wpb;
+    long long blocks_needed = (a->n_reps + wpb - 1) / wpb;
     long long grid = (long long)h->n_sms * h->blocks_per_sm[rng];
     if (grid > blocks_needed) grid = blocks_needed;
-    int rc = launch_sim(kp, h->policy, rng, (int)grid, h->warps_per_block * 32, h->smem_bytes, st);
+    int rc = launch_sim(kp, h->policy, rng, (int)grid, wpb * 32, h->smem_bytes[rng], st);
     if (rc != 0) return fail(rc, "simulation kernel launch failed (grid/block/shared-memory configuration)");
     return 0;
 }

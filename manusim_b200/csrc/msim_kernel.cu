@@ -84,13 +84,11 @@ struct Sim {
     // ------------------------------------------------------------------ event queues
     __device__ __forceinline__ void pushN(uint32_t ev) {
         ARR(uint32_t, nq)[nqt & (uint32_t)(p.lay.NQ - 1)] = ev;
-        nqt++;
-        if (nqt - nqh > (uint32_t)p.lay.NQ) status = MSIM_ST_FIFO_OVERFLOW;
-    }
+        nqt++;       // overflow is checked once per dispatched event (drain); the ring index is masked, so a
+    }                // transient overrun stays inside the slab and aborts the replication with a status code
     __device__ __forceinline__ void pushU(uint32_t ev) {
         ARR(uint32_t, uq)[uqt & (uint32_t)(p.lay.UQ - 1)] = ev;
         uqt++;
-        if (uqt - uqh > (uint32_t)p.lay.UQ) status = MSIM_ST_FIFO_OVERFLOW;
     }
     // env.timeout(delay) issued by a static process that owns calendar slot `slot`
     __device__ __forceinline__ void timer(int slot, float t, uint32_t ev) {
@@ -618,6 +616,7 @@ struct Sim {
                 return REQ_ADVANCE;
             }
             dispatch(ev);
+            if (nqt - nqh > (uint32_t)p.lay.NQ || uqt - uqh > (uint32_t)p.lay.UQ) status = MSIM_ST_FIFO_OVERFLOW;
             if (status) return REQ_DONE;
             if (nstage >= (uint32_t)kStageFlushAt) return REQ_FLUSH;
         }
@@ -681,7 +680,7 @@ __device__ __forceinline__ void warp_flush(const KParams& p, const unsigned char
 
 // ---------------------------------------------------------------------------------------------------------
 template <int POLICY, int RNG>
-__global__ void __launch_bounds__(256) sim_kernel(const __grid_constant__ KParams p) {
+__global__ void __launch_bounds__(256, 5) sim_kernel(const __grid_constant__ KParams p) {
     extern __shared__ __align__(16) unsigned char smem[];
     const Lay& L = p.lay;
     const int lane = threadIdx.x & 31;
@@ -704,21 +703,28 @@ __global__ void __launch_bounds__(256) sim_kernel(const __grid_constant__ KParam
         s.rep = rep;
 
         // ---- cooperative slab initialisation
+        #pragma unroll 1
         for (int i = lane; i < L.slab_bytes / 4; i += 32) reinterpret_cast<uint32_t*>(sb)[i] = 0u;
         __syncwarp();
+        #pragma unroll 1
         for (int i = lane; i < L.NT; i += 32) reinterpret_cast<float*>(sb + L.tm_time)[i] = CUDART_INF_F;
+        #pragma unroll 1
         for (int i = lane; i < L.MD; i += 32) {
             reinterpret_cast<float*>(sb + L.do_tt)[i] = CUDART_INF_F;
             (sb + L.do_next)[i] = (uint8_t)(i + 1 < L.MD ? i + 1 : kNone);
         }
+        #pragma unroll 1
         for (int i = lane; i < L.MP; i += 32) (sb + L.po_next)[i] = (uint8_t)(i + 1 < L.MP ? i + 1 : kNone);
+        #pragma unroll 1
         for (int i = lane; i < L.R; i += 32) {
             (sb + L.r_inh)[i] = kNone; (sb + L.r_int)[i] = kNone; (sb + L.r_outh)[i] = kNone; (sb + L.r_outt)[i] = kNone;
             reinterpret_cast<float*>(sb + L.r_lastq)[i] = CUDART_NAN_F;
         }
+        #pragma unroll 1
         for (int i = lane; i < L.P; i += 32) {
             (sb + L.p_obh)[i] = kNone; (sb + L.p_obt)[i] = kNone; (sb + L.p_fgqh)[i] = kNone; (sb + L.p_fgqt)[i] = kNone;
         }
+        #pragma unroll 1
         for (int i = lane; i < L.K; i += 32) {
             p.a.acc_sum[rep * L.K + i] = 0.0;
             p.a.acc_cnt[rep * L.K + i] = 0u;
@@ -761,6 +767,7 @@ __global__ void __launch_bounds__(256) sim_kernel(const __grid_constant__ KParam
             {
                 const float* tt = reinterpret_cast<const float*>(sb + L.tm_time);
                 const uint32_t* te = reinterpret_cast<const uint32_t*>(sb + L.tm_eid);
+#pragma unroll 1
                 for (int i = lane; i < L.NT; i += 32) {
                     unsigned long long k = ((unsigned long long)__float_as_uint(tt[i]) << 32) | te[i];
                     uint32_t kt = (uint32_t)(k >> 32), bt = (uint32_t)(best >> 32);
@@ -770,6 +777,7 @@ __global__ void __launch_bounds__(256) sim_kernel(const __grid_constant__ KParam
                 if (on_due) {
                     const float* dt = reinterpret_cast<const float*>(sb + L.do_tt);
                     const uint32_t* de = reinterpret_cast<const uint32_t*>(sb + L.do_eid);
+#pragma unroll 1
                     for (int i = lane; i < L.MD; i += 32) {
                         unsigned long long k = ((unsigned long long)__float_as_uint(dt[i]) << 32) | de[i];
                         uint32_t kt = (uint32_t)(k >> 32), bt = (uint32_t)(best >> 32);

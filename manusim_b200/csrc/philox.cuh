@@ -39,6 +39,12 @@ struct PhiloxStream {
 };
 
 #ifdef __CUDACC__
+// one out-of-line copy per kernel: the simulation kernel is instruction-cache bound, not ALU bound
+__device__ __noinline__ void philox_nl(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1,
+                                       uint32_t out[4]) {
+    philox4x32_10(c0, c1, c2, c3, k0, k1, out);
+}
+
 __device__ __forceinline__ float normal01(const uint32_t w[4]) {
     // Box-Muller on two of the four words
     float r = sqrtf(-2.0f * __logf(u01(w[0])));
@@ -46,12 +52,12 @@ __device__ __forceinline__ float normal01(const uint32_t w[4]) {
 }
 
 // Marsaglia-Tsang; iteration index is part of the counter so rejections stay reproducible
-__device__ __forceinline__ float gamma_mt(const PhiloxStream& s, float k, float theta) {
+__device__ __noinline__ float gamma_mt(const PhiloxStream s, float k, float theta) {
     float boost = 1.0f;
     float kk = k;
     uint32_t w[4];
     if (k < 1.0f) {
-        philox4x32_10(s.draw, s.stream, 0xFFFFu, 1u, s.k0, s.k1, w);
+        philox_nl(s.draw, s.stream, 0xFFFFu, 1u, s.k0, s.k1, w);
         boost = __powf(u01(w[0]), 1.0f / k);
         kk = k + 1.0f;
     }
@@ -59,7 +65,7 @@ __device__ __forceinline__ float gamma_mt(const PhiloxStream& s, float k, float 
     const float c = rsqrtf(9.0f * d);
     float out = d;
     for (uint32_t it = 0; it < 64u; ++it) {
-        philox4x32_10(s.draw, s.stream, it, 0u, s.k0, s.k1, w);
+        philox_nl(s.draw, s.stream, it, 0u, s.k0, s.k1, w);
         float x = normal01(w);
         float v = 1.0f + c * x;
         if (v <= 0.0f) continue;
@@ -78,15 +84,15 @@ __device__ __forceinline__ float sample_raw(const PhiloxStream& s, int kind, flo
     uint32_t w[4];
     switch (kind) {
     case 1: // uniform(a,b)
-        philox4x32_10(s.draw, s.stream, sub, 2u, s.k0, s.k1, w);
+        philox_nl(s.draw, s.stream, sub, 2u, s.k0, s.k1, w);
         return d0 + (d1 - d0) * u01(w[0]);
     case 2: case 3:
         return gamma_mt(s, d0, d1);
     case 4: // expo(mean)
-        philox4x32_10(s.draw, s.stream, sub, 2u, s.k0, s.k1, w);
+        philox_nl(s.draw, s.stream, sub, 2u, s.k0, s.k1, w);
         return -d0 * __logf(u01(w[0]));
     case 5: // normal(mu, sigma)
-        philox4x32_10(s.draw, s.stream, sub, 2u, s.k0, s.k1, w);
+        philox_nl(s.draw, s.stream, sub, 2u, s.k0, s.k1, w);
         return d0 + d1 * normal01(w);
     default:
         return d0;
@@ -94,13 +100,13 @@ __device__ __forceinline__ float sample_raw(const PhiloxStream& s, int kind, flo
 }
 
 // DistributionGenerator.random_number (utils.py:42-67): max(0, np.float32(v))
-__device__ __forceinline__ float draw_scalar_philox(const PhiloxStream& s, int kind, float d0, float d1) {
+__device__ __noinline__ float draw_scalar_philox(const PhiloxStream s, int kind, float d0, float d1) {
     float v = sample_raw(s, kind, d0, d1, 0u);
     return v > 0.0f ? v : 0.0f;
 }
 
 // DistributionGenerator.sum_random_numbers_batch (utils.py:69-102)
-__device__ __forceinline__ double draw_batch_philox(const PhiloxStream& s, int kind, float d0, float d1, double raw0,
+__device__ __noinline__ double draw_batch_philox(const PhiloxStream s, int kind, float d0, float d1, double raw0,
                                                     int count) {
     if (count <= 0) return 0.0;
     switch (kind) {

@@ -40,8 +40,10 @@ enum { MSIM_DELIVERY_AS_READY = 0, MSIM_DELIVERY_ON_DUE = 1, MSIM_DELIVERY_INSTA
 /* dispatch / release policies (compile-time device functions):
  *   FIFO          FactorySimulation.order_selection + scheduler   factory_sim.py:463-465, 180-193
  *   MAX_PRIORITY  NewSimulation.order_selection                   examples/simple_scheduler/simulation.py:31-44
- *   DBR           DBRSimulation.scheduler/order_selection         examples/toc_dbr/simulation.py:200-328 */
-enum { MSIM_POLICY_FIFO = 0, MSIM_POLICY_MAX_PRIORITY = 1, MSIM_POLICY_DBR = 2 };
+ *   DBR           DBRSimulation.scheduler/order_selection         examples/toc_dbr/simulation.py:200-328
+ *   EDD           extension (not in the reference): earliest ProductionOrder.duedate first (orders.py:11,
+ *                 factory_sim.py:188), FIFO among equal due dates; same machinery as MAX_PRIORITY */
+enum { MSIM_POLICY_FIFO = 0, MSIM_POLICY_MAX_PRIORITY = 1, MSIM_POLICY_DBR = 2, MSIM_POLICY_EDD = 3 };
 
 /* variate sources (BASELINE.json north_star "Random variates") */
 enum { MSIM_RNG_PHILOX = 0, MSIM_RNG_REPLAY = 1 };

@@ -14,7 +14,7 @@ import numpy as np
 
 DIST_KINDS = {"constant": 0, "uniform": 1, "gamma": 2, "erlang": 3, "expo": 4, "normal": 5}
 DELIVERY_MODES = {"asReady": 0, "onDue": 1, "instantly": 2}
-POLICIES = {"fifo": 0, "max_priority": 1, "dbr": 2}
+POLICIES = {"fifo": 0, "max_priority": 1, "dbr": 2, "edd": 3}
 
 PRODUCT_METRICS = ["deliveredOntime", "deliveredLate", "lostSales", "flowTime", "leadTime", "tardiness",
                    "earliness", "wip", "finishedGoods", "totalInventory", "released"]

@@ -67,8 +67,14 @@ extern "C" int msim_create(const msim_tables_t* t, msim_handle_t* out) {
     if (!(t->run_until > 0.0) || !(t->run_until > t->warmup) || t->warmup < 0.0)
         return fail(MSIM_E_INVALID, "need 0 <= warmup < run_until");
     if (t->delivery_mode < 0 || t->delivery_mode > 2) return fail(MSIM_E_INVALID, "bad delivery_mode");
-    if (t->policy != MSIM_POLICY_FIFO && t->policy != MSIM_POLICY_MAX_PRIORITY && t->policy != MSIM_POLICY_DBR)
-        return fail(MSIM_E_INVALID, "bad policy");
+    if (t->policy < MSIM_POLICY_FIFO || t->policy > MSIM_POLICY_EDD) return fail(MSIM_E_INVALID, "bad policy");
+    if (t->policy == MSIM_POLICY_DBR) {
+        if (!t->prod_shipping_buffer || !t->dbr_ccr_pt) return fail(MSIM_E_INVALID, "DBR needs shipping buffers and CCR times");
+        if (t->dbr_ccr < 0 || t->dbr_ccr >= R || !(t->dbr_interval > 0.0)) return fail(MSIM_E_INVALID, "bad DBR parameters");
+        for (int p = 0; p < P; ++p)
+            if (!(t->prod_shipping_buffer[p] > 0.0))   // FG.put(0) raises in _update_finished_goods (toc_dbr :71-73)
+                return fail(MSIM_E_INVALID, "DBR needs shipping_buffer > 0 for every product (SimPy Container.put(0) raises)");
+    }
     for (int p = 0; p < P; ++p) {
         int n = t->route_start[p + 1] - t->route_start[p];
         if (n < 1 || n > 250) return fail(MSIM_E_INVALID, "every product needs 1..250 route steps");
@@ -100,11 +106,11 @@ extern "C" int msim_create(const msim_tables_t* t, msim_handle_t* out) {
     L.MP = t->max_production_orders > 0 ? t->max_production_orders : 96;
     L.MD = t->max_demand_orders > 0 ? t->max_demand_orders : 96;
     L.NQ = t->fifo_capacity > 0 ? t->fifo_capacity : 64;
-    L.UQ = 16;
+    L.UQ = t->policy == MSIM_POLICY_DBR ? 64 : 16;          // a rope tick spawns up to P process_order Initialize events
     if (L.MP > 250 || L.MD > 250 || (L.NQ & (L.NQ - 1))) { delete h; return fail(MSIM_E_INVALID, "bad pool capacities"); }
     L.K = 11 * P + 4 * R + 3;
     const bool dbr = t->policy == MSIM_POLICY_DBR;
-    const bool prio = t->policy != MSIM_POLICY_FIFO;
+    const bool prio = t->policy == MSIM_POLICY_MAX_PRIORITY || t->policy == MSIM_POLICY_EDD;
     const bool on_due = t->delivery_mode == MSIM_DELIVERY_ON_DUE;
 
     // ---- per-replication slab layout
@@ -115,6 +121,7 @@ extern "C" int msim_create(const msim_tables_t* t, msim_handle_t* out) {
     L.uq = take(L.UQ * 4, 4);
     L.tm_time = take(L.NT * 4, 4);
     L.tm_eid = take(L.NT * 4, 4);
+    L.r_tpy = dbr ? take(R * 8, 8) : 0; L.r_start_d = dbr ? take(R * 8, 8) : 0; L.r_utf_d = dbr ? take(R * 8, 8) : 0;
     L.r_utf = take(R * 4, 4); L.r_tbf = take(R * 4, 4); L.r_setup = take(R * 4, 4); L.r_start = take(R * 4, 4);
     L.r_busy = take(R * 4, 4); L.r_qq = take(R * 4, 4); L.r_lastq = take(R * 4, 4);
     L.p_fg = take(P * 4, 4); L.p_wip = take(P * 4, 4); L.p_fgc = take(P * 4, 4); L.p_dqty = take(P * 4, 4);
@@ -125,6 +132,7 @@ extern "C" int msim_create(const msim_tables_t* t, msim_handle_t* out) {
     L.do_arr = take(L.MD * 4, 4); L.do_due = take(L.MD * 4, 4); L.do_qty = take(L.MD * 4, 4);
     L.do_tt = take(L.MD * 4, 4);               // kept for every mode: the calendar scan reads it only for onDue
     L.do_eid = on_due ? take(L.MD * 4, 4) : 0;
+    L.r_flags = dbr ? take(R, 1) : 0; L.po_relpy = dbr ? take(L.MP, 1) : 0;
     L.r_phase = take(R, 1); L.r_cur = take(R, 1); L.r_tcur = take(R, 1);
     L.r_inh = take(R, 1); L.r_int = take(R, 1); L.r_outh = take(R, 1); L.r_outt = take(R, 1);
     L.p_obh = take(P, 1); L.p_obt = take(P, 1); L.p_fgqh = take(P, 1); L.p_fgqt = take(P, 1);
@@ -180,6 +188,7 @@ extern "C" int msim_create(const msim_tables_t* t, msim_handle_t* out) {
     KParams& kp = h->kp;
     kp.run_until = (float)t->run_until;
     kp.warmup = (float)t->warmup;
+    kp.warmup_d = t->warmup;
     kp.delivery_mode = t->delivery_mode;
     kp.log_queues = t->log_queues ? 1 : 0;
     kp.dbr_ccr = t->dbr_ccr; kp.dbr_repair = t->dbr_repair;

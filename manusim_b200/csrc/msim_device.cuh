@@ -35,10 +35,13 @@ struct Scal {
     uint8_t inb_head, inb_tail;   // inbound_demand_orders items (linked through do_next)
     uint8_t po_free, do_free;     // free lists
     uint8_t pad[3];
-    // DBR
-    double cb_level;
-    uint8_t fwd_wait, drain_wait, fin_head, fin_tail;
-    uint8_t pad2[4];
+    // DBR (examples/toc_dbr/simulation.py)
+    double tick_d;          // exact python-typed time of the pending rope tick
+    float cb_level;         // constraint_buffer_level (:52, :285, :188)
+    uint8_t fwd_wait;       // _process_demandOrders blocked on inbound.get()
+    uint8_t drain_wait;     // _update_constraint_buffer blocked on resource_finished[CCR].get()
+    uint8_t fin_n;          // items in resource_finished[CCR]
+    uint8_t fin[5];
 };
 
 // byte offsets of every per-replication array inside the warp's shared-memory slab and of every table
@@ -51,6 +54,7 @@ struct Lay {
     int32_t p_fg, p_wip, p_fgc, p_dqty, p_ddue;
     int32_t po_rel, po_qty, po_prio, po_tt, po_eid, po_ccr;
     int32_t do_arr, do_due, do_qty, do_tt, do_eid;
+    int32_t r_tpy, r_start_d, r_utf_d, r_flags, po_relpy;   // DBR: python-typed clock excursions (Appendix B.2)
     int32_t r_phase, r_cur, r_tcur, r_inh, r_int, r_outh, r_outt;
     int32_t p_obh, p_obt, p_fgqh, p_fgqt;
     int32_t po_prod, po_done, po_next, po_loc, do_prod, do_next;
@@ -69,6 +73,7 @@ struct KParams {
     // DBR
     int32_t dbr_ccr, dbr_repair;
     double dbr_interval, dbr_cb_target, dbr_release_limit, dbr_ccr_limit, dbr_min_lot, dbr_ccr_setup;
+    double warmup_d;               // exact (python-typed) warm-up instant
     int32_t warps_per_block, _pad;
     msim_run_args_t a;             // device pointers
 };

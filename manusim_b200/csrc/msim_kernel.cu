@@ -39,11 +39,15 @@ enum Op : uint32_t {
     OP_TRANS_GOT, OP_TRANS_PUT, OP_TRANS_GOT2_FINAL, OP_TRANS_GOT2_NEXT, OP_TRANS_FGPUT, OP_TRANS_WIPGET,
     OP_TRANS_PUTIN,
     OP_DELIV_GOT, OP_INIT_SHIP, OP_TO_SHIP, OP_SHIP_GOT,
+    // DBR (examples/toc_dbr/simulation.py)
+    OP_TO_TICK, OP_INIT_DORDER, OP_TO_DORDER, OP_SEED_PUT, OP_FIN_PUT, OP_DRAIN_GOT,
 };
 
 enum Phase : uint8_t { PH_SETUP = 0, PH_PROC = 1, PH_TTR = 2 };
 enum Loc : uint8_t { LOC_NONE = 0, LOC_IN = 1, LOC_PROC = 2, LOC_OUT = 3, LOC_TRANS = 4 };
-enum Req : int { REQ_ADVANCE = 0, REQ_FLUSH = 1, REQ_DONE = 2 };
+enum Req : int { REQ_ADVANCE = 0, REQ_FLUSH = 1, REQ_DONE = 2, REQ_SELECT = 3 };
+// DBR per-resource flags: python-typed (int / float64) values of the dynamically typed clock (Appendix B.2)
+enum { F_TIMER_PY = 1, F_START_PY = 2, F_UTF_PY = 4 };
 
 // product / resource / general metric indices (enum order of metrics.py:43-67)
 enum { PM_ONTIME = 0, PM_LATE, PM_LOST, PM_FLOW, PM_LEAD, PM_TARDY, PM_EARLY, PM_WIP, PM_FG, PM_INV, PM_RELEASED };
@@ -54,6 +58,11 @@ __device__ __forceinline__ uint32_t EV(uint32_t op, uint32_t a, uint32_t b) { re
 
 // round(np.float32 x, 6)  (factory_sim.py:284,443)
 __device__ __forceinline__ float round6(float x) { return __fdiv_rn(rintf(__fmul_rn(x, 1e6f)), 1e6f); }
+// round(np.float32 x, 3)  (toc_dbr/simulation.py:229-236)
+__device__ __forceinline__ float round3(float x) { return __fdiv_rn(rintf(__fmul_rn(x, 1e3f)), 1e3f); }
+// round(python float x, 6): correctly rounded decimal in CPython; rint(x*1e6)/1e6 differs only when x*1e6 lands
+// within one ulp of a half-way point (documented deviation)
+__device__ __forceinline__ double pyround6(double x) { return __ddiv_rn(rint(__dmul_rn(x, 1e6)), 1e6); }
 
 template <int POLICY, int RNG>
 struct Sim {
@@ -70,6 +79,12 @@ struct Sim {
     uint32_t nev, tseq, same_left;
     int status;
     uint32_t pending;
+    // DBR only: exact python-typed clock (now is its float32 view) and the pending cooperative dispatch request
+    double now_d;
+    uint32_t now_py;
+    uint32_t sel_req;
+    static constexpr bool DBR = POLICY == MSIM_POLICY_DBR;
+    static constexpr bool PRIO = POLICY == MSIM_POLICY_MAX_PRIORITY || POLICY == MSIM_POLICY_EDD;
 
     __device__ __forceinline__ Sim(const KParams& p_, unsigned char* sb_, const unsigned char* tb_)
         : p(p_), sb(sb_), tb(tb_) { sc = reinterpret_cast<Scal*>(sb + p.lay.scal); }
@@ -188,6 +203,7 @@ struct Sim {
         uint32_t i = sc->po_free;
         if (i == kNone) { status = MSIM_ST_PO_POOL_OVERFLOW; return 0; }
         sc->po_free = ARR(uint8_t, po_next)[i];
+        if (DBR) ARR(float, po_tt)[i] = CUDART_INF_F;
         return i;
     }
     __device__ __forceinline__ void free_po(uint32_t i) {
@@ -297,7 +313,12 @@ struct Sim {
         uint32_t h = ARR(uint8_t, r_inh)[r];
         if (h == kNone) { sc->mach_wait |= 1u << r; return; }   // plain get() on an empty queue
         uint32_t pick = h;
-        if (POLICY == MSIM_POLICY_MAX_PRIORITY) {
+        if (DBR) {
+            // buffer-penetration dispatch (toc_dbr/simulation.py:291-328) needs a scan of every in-flight order:
+            // a single queued order is trivially the minimum, otherwise the whole warp computes the priorities
+            if (ARR(uint8_t, po_next)[h] != kNone) { sel_req = (uint32_t)r + 1u; return; }
+            list_pop(ARR(uint8_t, r_inh) + r, ARR(uint8_t, r_int) + r, ARR(uint8_t, po_next));
+        } else if (PRIO) {
             // max(orders, key=priority): first maximum in queue order (simple_scheduler/simulation.py:36)
             const uint8_t* nx = ARR(uint8_t, po_next);
             const float* pr = ARR(float, po_prio);
@@ -325,6 +346,7 @@ struct Sim {
             ARR(float, r_start)[r] = now;                                  // breakdown_start, :272
             float ttr = draw_scalar(3, TAB(DDist, t_ttr)[r]);              // :275
             ARR(uint8_t, r_phase)[r] = PH_TTR;
+            if (DBR) ARR(uint8_t, r_flags)[r] &= ~F_TIMER_PY;
             timer(r, __fadd_rn(now, ttr), EV(OP_TO_TTR, r, 0));
             return;
         }
@@ -363,12 +385,15 @@ struct Sim {
             break;
         case OP_SCHED_GOT: {                                     // scheduler :183-193
             int prod = ARR(uint8_t, do_prod)[b];
-            uint32_t po = alloc_po();
-            if (status) break;
-            ARR(uint8_t, po_prod)[po] = (uint8_t)prod;
-            ARR(float, po_qty)[po] = ARR(float, do_qty)[b];
-            if (POLICY == MSIM_POLICY_MAX_PRIORITY) ARR(float, po_prio)[po] = 0.0f;
-            pushU(EV(OP_INIT_RELEASE, 0, po));
+            if (!DBR) {           // DBR: _process_demandOrders only forwards (toc_dbr/simulation.py:408-412)
+                uint32_t po = alloc_po();
+                if (status) break;
+                ARR(uint8_t, po_prod)[po] = (uint8_t)prod;
+                ARR(float, po_qty)[po] = ARR(float, do_qty)[b];
+                if (POLICY == MSIM_POLICY_MAX_PRIORITY) ARR(float, po_prio)[po] = 0.0f;
+                if (POLICY == MSIM_POLICY_EDD) ARR(float, po_prio)[po] = -ARR(float, do_due)[b];
+                pushU(EV(OP_INIT_RELEASE, 0, po));
+            }
             list_append(ARR(uint8_t, p_obh) + prod, ARR(uint8_t, p_obt) + prod, ARR(uint8_t, do_next), b);
             pushN(EV(OP_PUT_OUTBOUND, prod, 0));
             break;
@@ -386,6 +411,7 @@ struct Sim {
             int first = TAB(uint8_t, t_step_res)[TAB(uint16_t, t_route_start)[prod]];
             ARR(uint8_t, po_done)[b] = 0;
             ARR(float, po_rel)[b] = now;
+            if (DBR) ARR(uint8_t, po_relpy)[b] = (uint8_t)now_py;
             list_append(ARR(uint8_t, r_inh) + first, ARR(uint8_t, r_int) + first, ARR(uint8_t, po_next), b);
             ARR(uint8_t, po_loc)[b] = LOC_IN;
             pushN(EV(OP_REL_PUT1, first, b));
@@ -434,6 +460,7 @@ struct Sim {
         }
         case OP_MACH_REQ:                                        // :423
             ARR(uint8_t, r_phase)[a] = PH_SETUP;
+            if (DBR) ARR(uint8_t, r_flags)[a] &= ~F_TIMER_PY;
             timer(a, __fadd_rn(now, ARR(float, r_setup)[a]), EV(OP_TO_SETUP, a, 0));
             break;
         case OP_TO_SETUP: {                                      // :425-440
@@ -444,14 +471,49 @@ struct Sim {
             double total = draw_batch(TAB(DDist, t_step_dist)[step], (int)ARR(float, po_qty)[po]);
             if (total < 0.0) { status = MSIM_ST_NEGATIVE_DELAY; break; }
             ARR(uint8_t, r_phase)[a] = PH_PROC;
+            if (DBR) {
+                uint8_t fl = ARR(uint8_t, r_flags)[a] & ~(F_TIMER_PY | F_START_PY);
+                if (now_py) {
+                    // python-typed clock + python float delay: the sum stays a python float (float64)
+                    fl |= F_START_PY;
+                    ARR(double, r_start_d)[a] = now_d;
+                    double td = __dadd_rn(now_d, total);
+                    if (td == now_d) {
+                        ARR(uint8_t, r_flags)[a] = fl;
+                        pushN(EV(OP_TO_PROC, a, 0));
+                    } else {
+                        ARR(double, r_tpy)[a] = td;
+                        ARR(float, tm_time)[a] = __double2float_rn(td);
+                        ARR(uint32_t, tm_eid)[a] = tseq++;
+                        ARR(uint8_t, r_flags)[a] = fl | F_TIMER_PY;
+                    }
+                    break;
+                }
+                ARR(uint8_t, r_flags)[a] = fl;
+            }
             timer(a, __fadd_rn(now, __double2float_rn(total)), EV(OP_TO_PROC, a, 0));
             break;
         }
         case OP_TO_PROC: {                                       // :442-451
             uint32_t po = ARR(uint8_t, r_cur)[a];
-            float busy = round6(__fsub_rn(now, ARR(float, r_start)[a]));
+            float busy;
+            if (DBR && now_py && (ARR(uint8_t, r_flags)[a] & F_START_PY)) {
+                // both ends python-typed: float64 subtraction and python round (factory_sim.py:443)
+                double bd = pyround6(__dsub_rn(now_d, ARR(double, r_start_d)[a]));
+                busy = __double2float_rn(bd);
+                if (ARR(uint8_t, r_flags)[a] & F_UTF_PY) {
+                    double u = __dadd_rn(ARR(double, r_utf_d)[a], bd);
+                    ARR(double, r_utf_d)[a] = u;
+                    ARR(float, r_utf)[a] = __double2float_rn(u);
+                } else {
+                    ARR(float, r_utf)[a] = __fadd_rn(ARR(float, r_utf)[a], busy);
+                }
+            } else {
+                busy = round6(__fsub_rn(now, ARR(float, r_start)[a]));
+                ARR(float, r_utf)[a] = __fadd_rn(ARR(float, r_utf)[a], busy);
+                if (DBR) ARR(uint8_t, r_flags)[a] &= ~F_UTF_PY;
+            }
             ARR(float, r_busy)[a] = busy;
-            ARR(float, r_utf)[a] = __fadd_rn(ARR(float, r_utf)[a], busy);
             ARR(uint8_t, po_done)[po]++;
             ARR(uint8_t, po_loc)[po] = LOC_NONE;
             pushN(EV(OP_MACH_GOTPROC, a, 0));
@@ -471,6 +533,10 @@ struct Sim {
                 sc->trans_wait &= ~(1u << a);
                 pushN(EV(OP_TRANS_GOT, a, po));
             }
+            if (DBR && p.dbr_repair && a == p.dbr_ccr) {        // patch P3: stores.resource_finished[CCR].put(po)
+                if (sc->fin_n < 5) sc->fin[sc->fin_n++] = ARR(uint8_t, r_cur)[a]; else status = MSIM_ST_FIFO_OVERFLOW;
+                pushN(EV(OP_FIN_PUT, 0, 0));
+            }
             if (warm) emit(ringR(RM_UTIL, a), now, ARR(float, r_busy)[a]);
             nev++;                                               // Release event of the `with` block
             mach_loop_top(a);
@@ -479,6 +545,7 @@ struct Sim {
             if (warm) emit(ringR(RM_BREAKDOWN, a), ARR(float, r_start)[a], round6(__fsub_rn(now, ARR(float, r_start)[a])));
             ARR(float, r_tbf)[a] = draw_scalar(3, TAB(DDist, t_tbf)[a]);
             ARR(float, r_utf)[a] = 0.0f;
+            if (DBR) { ARR(double, r_utf_d)[a] = 0.0; ARR(uint8_t, r_flags)[a] |= F_UTF_PY; }   // the int 0
             mach_select(a);
             break;
         case OP_TRANS_GOT:                                       // _transportation :300-304
@@ -524,7 +591,10 @@ struct Sim {
             ARR(float, p_fgc)[prod] = f;
             sc->fgc_sum = __fadd_rn(sc->fgc_sum, __fsub_rn(f, old));
             if (warm) {
-                emit(ringP(PM_FLOW, prod), now, __fsub_rn(now, ARR(float, po_rel)[po]));
+                float flow = __fsub_rn(now, ARR(float, po_rel)[po]);
+                if (DBR && now_py && ARR(uint8_t, po_relpy)[po])
+                    flow = __double2float_rn(__dsub_rn(now_d, (double)ARR(float, po_rel)[po]));
+                emit(ringP(PM_FLOW, prod), now, flow);
                 inventory(prod, true, true);
             }
             free_po(po);
@@ -592,9 +662,123 @@ struct Sim {
             nev++;                                               // process-end event
             free_do(b);
             break;
+        case OP_TO_TICK:                                         // DBRSimulation.scheduler, toc_dbr/simulation.py:200-275
+            if (DBR) rope_tick();
+            break;
+        case OP_INIT_DORDER:                                     // process_order :277-283
+            if (DBR) {
+                float sched = ARR(float, po_tt)[b];
+                ARR(float, po_tt)[b] = CUDART_INF_F;
+                if (sched > now) {
+                    float t = __fadd_rn(now, __fsub_rn(sched, now));
+                    if (t == now) {
+                        pushN(EV(OP_TO_DORDER, 0, b));
+                    } else {
+                        ARR(float, po_tt)[b] = t;
+                        ARR(uint32_t, po_eid)[b] = tseq++;
+                    }
+                } else {
+                    dorder_go(b);
+                }
+            }
+            break;
+        case OP_TO_DORDER:                                       // process_order :284-289
+            if (DBR) dorder_go(b);
+            break;
+        case OP_SEED_PUT:                                        // _update_finished_goods :71-73, ContainerPut processed
+            serve_fg(a);
+            nev++;                                               // process-end event
+            break;
+        case OP_FIN_PUT:                                         // StorePut[resource_finished[CCR]] processed
+            if (DBR && sc->drain_wait && sc->fin_n) {
+                uint32_t po = sc->fin[0];
+                for (int i = 1; i < sc->fin_n; ++i) sc->fin[i - 1] = sc->fin[i];
+                sc->fin_n--;
+                sc->drain_wait = 0;
+                pushN(EV(OP_DRAIN_GOT, 0, po));
+            }
+            break;
+        case OP_DRAIN_GOT:                                       // _update_constraint_buffer :173-190
+            if (DBR) {
+                int prod = ARR(uint8_t, po_prod)[b];
+                int step = TAB(uint16_t, t_route_start)[prod] + ARR(uint8_t, po_done)[b] - 1;
+                float mean_pt = __double2float_rn(TAB(DDist, t_step_dist)[step].raw0);
+                float ccr_time = __fadd_rn(__fmul_rn(mean_pt, ARR(float, po_qty)[b]), __double2float_rn(p.dbr_ccr_setup));
+                sc->cb_level = __fsub_rn(sc->cb_level, ccr_time);
+                if (sc->fin_n) {
+                    uint32_t po = sc->fin[0];
+                    for (int i = 1; i < sc->fin_n; ++i) sc->fin[i - 1] = sc->fin[i];
+                    sc->fin_n--;
+                    pushN(EV(OP_DRAIN_GOT, 0, po));
+                } else {
+                    sc->drain_wait = 1;
+                }
+            }
+            break;
         default:
             break;
         }
+    }
+
+    // process_order continuation: constraint_buffer_level += ccr_add; env.process(_release_order(po))
+    __device__ __forceinline__ void dorder_go(int po) {
+        sc->cb_level = __fadd_rn(sc->cb_level, ARR(float, po_ccr)[po]);
+        pushU(EV(OP_INIT_RELEASE, 0, po));
+        nev++;                                                   // process-end event
+    }
+
+    // one rope tick (toc_dbr/simulation.py:206-275); runs at python-int instants 0, interval, 2*interval, ...
+    __device__ __forceinline__ void rope_tick() {
+        const int P = p.lay.P;
+        float rpr[32], qty[32];
+        uint8_t ord[32];
+        for (int i = 0; i < P; ++i) {
+            float target = __double2float_rn(TAB(double, t_shipbuf)[i]);
+            float have = __fadd_rn(ARR(float, p_wip)[i], ARR(float, p_fg)[i]);
+            float repl = __fsub_rn(target, have);
+            if (!(repl > 0.0f)) repl = 0.0f;
+            float lot = __double2float_rn(p.dbr_min_lot);
+            qty[i] = repl >= lot ? repl : lot;                  // max(replenishment, min_lotsize)
+            float key = round3(__fdiv_rn(repl, target));
+            int j = i;                                           // stable insertion, descending release priority
+            while (j > 0 && rpr[j - 1] < key) { rpr[j] = rpr[j - 1]; ord[j] = ord[j - 1]; --j; }
+            rpr[j] = key; ord[j] = (uint8_t)i;
+        }
+        float room = p.dbr_ccr_limit != 0.0 ? __double2float_rn(p.dbr_interval * p.dbr_ccr_limit)
+                                            : __fsub_rn(__double2float_rn(p.dbr_cb_target), sc->cb_level);
+        if (room > 0.0f) {
+            double n_rel = 0.0;
+            for (int k = 0; k < P; ++k) {
+                int i = ord[k];
+                double cpt = TAB(double, t_ccrpt)[i];
+                float ccr_t = 0.0f, sched = now;
+                bool go = false;
+                if (cpt > 0.0) {
+                    if (room > 0.0f && n_rel < p.dbr_release_limit) {
+                        ccr_t = __fadd_rn(__fmul_rn(qty[i], __double2float_rn(cpt)), __double2float_rn(p.dbr_ccr_setup));
+                        sched = __fadd_rn(now, ccr_t);
+                        go = true;
+                        n_rel += 1.0;
+                    }
+                } else {
+                    go = true;
+                }
+                if (qty[i] > 0.0f && go) {
+                    uint32_t po = alloc_po();
+                    if (status) return;
+                    ARR(uint8_t, po_prod)[po] = (uint8_t)i;
+                    ARR(float, po_qty)[po] = qty[i];
+                    ARR(float, po_tt)[po] = sched;               // holds `schedule` until Initialize[process_order]
+                    ARR(float, po_ccr)[po] = ccr_t;
+                    pushU(EV(OP_INIT_DORDER, 0, po));
+                    room = __fsub_rn(room, ccr_t);
+                }
+            }
+        }
+        double nt = __dadd_rn(now_d, p.dbr_interval);            // yield env.timeout(scheduler_interval)
+        sc->tick_d = nt;
+        ARR(float, tm_time)[p.lay.R + p.lay.P + 1] = __double2float_rn(nt);
+        ARR(uint32_t, tm_eid)[p.lay.R + p.lay.P + 1] = tseq++;
     }
 
     // lane 0: run zero-delay events until the warp has to cooperate again
@@ -616,6 +800,7 @@ struct Sim {
                 return REQ_ADVANCE;
             }
             dispatch(ev);
+            if (DBR && sel_req) return status ? REQ_DONE : REQ_SELECT;
             if (nqt - nqh > (uint32_t)p.lay.NQ || uqt - uqh > (uint32_t)p.lay.UQ) status = MSIM_ST_FIFO_OVERFLOW;
             if (status) return REQ_DONE;
             if (nstage >= (uint32_t)kStageFlushAt) return REQ_FLUSH;
@@ -628,6 +813,7 @@ struct Sim {
         const int R = p.lay.R, P = p.lay.P;
         now = 0.0f; warm = 0; nqh = nqt = uqh = uqt = 0; nstage = 0; logc = 0; nev = 0; tseq = 0; same_left = 0;
         status = 0; pending = 0;
+        now_d = 0.0; now_py = 1; sel_req = 0;
         for (int r = 0; r < R; ++r) {                            // _start_resources :248-261 (draws at construction)
             const DDist& tb_ = TAB(DDist, t_tbf)[r];
             ARR(float, r_tbf)[r] = tb_.kind == MSIM_DIST_NONE ? CUDART_INF_F : draw_scalar(3, tb_);
@@ -643,6 +829,21 @@ struct Sim {
             nev += 2;                                            // Initialize[_generate_demand_orders], Initialize[_delivery_orders]
             demand_draw(prod);
             sc->deliv_wait |= 1u << prod;
+        }
+        if (DBR) {                                               // _start_custom_process, toc_dbr/simulation.py:37-47
+            for (int r = 0; r < R; ++r) ARR(uint8_t, r_flags)[r] = F_UTF_PY;
+            nev += 2;                                            // Initialize[_update_constraint_buffer], [_process_demandOrders]
+            sc->drain_wait = 1;
+            sc->sched_wait = 1;                                  // the forwarder is the getter of inbound_demand_orders
+            for (int prod = 0; prod < P; ++prod) {               // Initialize[_update_finished_goods(p)]: FG.put(shipping_buffer)
+                nev++;
+                float sbuf = __double2float_rn(TAB(double, t_shipbuf)[prod]);
+                if (!(sbuf > 0.0f)) { status = MSIM_ST_AMOUNT_NONPOSITIVE; return; }
+                ARR(float, p_fg)[prod] = sbuf;
+                pushN(EV(OP_SEED_PUT, prod, 0));
+            }
+            pending = EV(OP_TO_TICK, 0, 0);                      // Initialize[scheduler] (the rope): first tick at t = 0,
+            return;                                              // counted and executed by dispatch before any NORMAL event
         }
         nev++;                                                   // Initialize[scheduler]
         sc->sched_wait = 1;
@@ -693,6 +894,7 @@ __global__ void __launch_bounds__(256, 5) sim_kernel(const __grid_constant__ KPa
     Sim<POLICY, RNG> s(p, sb, smem);
     Scal* sc = s.sc;
     const bool on_due = p.delivery_mode == MSIM_DELIVERY_ON_DUE;
+    constexpr bool DBR = POLICY == MSIM_POLICY_DBR;
     const uint32_t until_bits = __float_as_uint(p.run_until);
 
     for (;;) {
@@ -714,7 +916,10 @@ __global__ void __launch_bounds__(256, 5) sim_kernel(const __grid_constant__ KPa
             (sb + L.do_next)[i] = (uint8_t)(i + 1 < L.MD ? i + 1 : kNone);
         }
         #pragma unroll 1
-        for (int i = lane; i < L.MP; i += 32) (sb + L.po_next)[i] = (uint8_t)(i + 1 < L.MP ? i + 1 : kNone);
+        for (int i = lane; i < L.MP; i += 32) {
+            (sb + L.po_next)[i] = (uint8_t)(i + 1 < L.MP ? i + 1 : kNone);
+            if (DBR) reinterpret_cast<float*>(sb + L.po_tt)[i] = CUDART_INF_F;
+        }
         #pragma unroll 1
         for (int i = lane; i < L.R; i += 32) {
             (sb + L.r_inh)[i] = kNone; (sb + L.r_int)[i] = kNone; (sb + L.r_outh)[i] = kNone; (sb + L.r_outt)[i] = kNone;
@@ -731,7 +936,6 @@ __global__ void __launch_bounds__(256, 5) sim_kernel(const __grid_constant__ KPa
         }
         if (lane == 0) {
             sc->inb_head = kNone; sc->inb_tail = kNone; sc->po_free = 0; sc->do_free = 0;
-            sc->fin_head = kNone; sc->fin_tail = kNone;
             if (RNG == MSIM_RNG_REPLAY) {
                 long long oa = p.a.tape_A_off[rep], ob = p.a.tape_B_off[rep], oc = p.a.tape_C_off[rep], od = p.a.tape_D_off[rep];
                 sc->tbase[0] = p.a.tape_A + oa; sc->tlen[0] = (uint32_t)(p.a.tape_A_off[rep + 1] - oa);
@@ -760,6 +964,44 @@ __global__ void __launch_bounds__(256, 5) sim_kernel(const __grid_constant__ KPa
                 continue;
             }
             if (req == REQ_DONE) break;
+            if (DBR && req == REQ_SELECT) {
+                // ---- cooperative DBR dispatch (toc_dbr/simulation.py:291-328): for every queued order, the
+                // quantity of same-product orders released strictly earlier that sit in ANY input/output/transport/
+                // processing store, plus the FG level, over the shipping buffer; first minimum wins.
+                const int r = __shfl_sync(FULLMASK, (int)s.sel_req, 0) - 1;
+                const uint8_t* nx = sb + L.po_next;
+                const uint8_t* prd = sb + L.po_prod;
+                const uint8_t* loc = sb + L.po_loc;
+                const float* rel = reinterpret_cast<const float*>(sb + L.po_rel);
+                const float* qty = reinterpret_cast<const float*>(sb + L.po_qty);
+                const float* fg = reinterpret_cast<const float*>(sb + L.p_fg);
+                const double* sbuf = reinterpret_cast<const double*>(smem + L.t_shipbuf);
+                uint32_t best = kNone, best_prev = kNone, prev = kNone;
+                float best_pr = 0.0f;
+#pragma unroll 1
+                for (uint32_t o = (sb + L.r_inh)[r]; o != kNone; prev = o, o = nx[o]) {
+                    const int op = prd[o];
+                    const float ro = rel[o];
+                    float part = 0.0f;
+#pragma unroll 1
+                    for (int i = lane; i < L.MP; i += 32)
+                        if (loc[i] != LOC_NONE && prd[i] == op && rel[i] < ro) part += qty[i];
+#pragma unroll
+                    for (int off = 16; off > 0; off >>= 1) part += __shfl_xor_sync(FULLMASK, part, off);
+                    const float pr = __fdiv_rn(__fadd_rn(part, fg[op]), __double2float_rn(sbuf[op]));
+                    if (best == kNone || pr < best_pr) { best = o; best_pr = pr; best_prev = prev; }
+                }
+                if (lane == 0) {
+                    uint8_t* nxw = sb + L.po_next;
+                    if (best_prev == kNone) (sb + L.r_inh)[r] = nxw[best]; else nxw[best_prev] = nxw[best];
+                    if (nxw[best] == kNone) (sb + L.r_int)[r] = (uint8_t)best_prev;
+                    (sb + L.po_loc)[best] = LOC_NONE;
+                    s.pushN(EV(OP_MACH_GOT, (uint32_t)r, best));
+                    s.sel_req = 0;
+                }
+                __syncwarp();
+                continue;
+            }
 
             // ---- cooperative next-event selection: min over (time, eid) of every calendar slot
             unsigned long long best = ~0ull;
@@ -785,6 +1027,17 @@ __global__ void __launch_bounds__(256, 5) sim_kernel(const __grid_constant__ KPa
                         if (k < best) { best = k; slot = L.NT + i; }
                     }
                 }
+                if (DBR) {
+                    const float* pt = reinterpret_cast<const float*>(sb + L.po_tt);
+                    const uint32_t* pe = reinterpret_cast<const uint32_t*>(sb + L.po_eid);
+#pragma unroll 1
+                    for (int i = lane; i < L.MP; i += 32) {
+                        unsigned long long k = ((unsigned long long)__float_as_uint(pt[i]) << 32) | pe[i];
+                        uint32_t kt = (uint32_t)(k >> 32), bt = (uint32_t)(best >> 32);
+                        if (kt == bt) cnt++; else if (kt < bt) cnt = 1;
+                        if (k < best) { best = k; slot = L.NT + L.MD + i; }
+                    }
+                }
             }
 #pragma unroll
             for (int off = 16; off > 0; off >>= 1) {
@@ -806,20 +1059,35 @@ __global__ void __launch_bounds__(256, 5) sim_kernel(const __grid_constant__ KPa
                 }
                 sc->n_timeouts++;
                 uint32_t ev;
+                if (DBR) s.now_py = 0;     // Environment._now takes the type of the popped entry (Appendix B.2)
                 if (slot < L.R) {
                     uint8_t ph = (sb + L.r_phase)[slot];
                     ev = EV(ph == PH_SETUP ? OP_TO_SETUP : (ph == PH_PROC ? OP_TO_PROC : OP_TO_TTR), slot, 0);
                     reinterpret_cast<float*>(sb + L.tm_time)[slot] = CUDART_INF_F;
+                    if (DBR && ((sb + L.r_flags)[slot] & F_TIMER_PY)) {
+                        s.now_py = 1;
+                        s.now_d = reinterpret_cast<const double*>(sb + L.r_tpy)[slot];
+                    }
                 } else if (slot < L.R + L.P) {
                     ev = EV(OP_TO_DEMAND, slot - L.R, 0);
                     reinterpret_cast<float*>(sb + L.tm_time)[slot] = CUDART_INF_F;
                 } else if (slot < L.NT) {
-                    ev = EV(OP_TO_WARMUP, 0, 0);
                     reinterpret_cast<float*>(sb + L.tm_time)[slot] = CUDART_INF_F;
-                } else {
+                    if (slot == L.R + L.P) {
+                        ev = EV(OP_TO_WARMUP, 0, 0);
+                        if (DBR) { s.now_py = 1; s.now_d = p.warmup_d; }
+                    } else {
+                        ev = EV(OP_TO_TICK, 0, 0);
+                        if (DBR) { s.now_py = 1; s.now_d = sc->tick_d; }
+                    }
+                } else if (slot < L.NT + L.MD) {
                     int d = slot - L.NT;
                     ev = EV(OP_TO_SHIP, (sb + L.do_prod)[d], d);
                     reinterpret_cast<float*>(sb + L.do_tt)[d] = CUDART_INF_F;
+                } else {
+                    int po = slot - L.NT - L.MD;
+                    ev = EV(OP_TO_DORDER, 0, po);
+                    reinterpret_cast<float*>(sb + L.po_tt)[po] = CUDART_INF_F;
                 }
                 s.pending = ev;
             }
@@ -916,6 +1184,12 @@ static sim_fn pick(int policy, int rng) {
     if (policy == MSIM_POLICY_MAX_PRIORITY)
         return rng == MSIM_RNG_REPLAY ? sim_kernel<MSIM_POLICY_MAX_PRIORITY, MSIM_RNG_REPLAY>
                                       : sim_kernel<MSIM_POLICY_MAX_PRIORITY, MSIM_RNG_PHILOX>;
+    if (policy == MSIM_POLICY_DBR)
+        return rng == MSIM_RNG_REPLAY ? sim_kernel<MSIM_POLICY_DBR, MSIM_RNG_REPLAY>
+                                      : sim_kernel<MSIM_POLICY_DBR, MSIM_RNG_PHILOX>;
+    if (policy == MSIM_POLICY_EDD)
+        return rng == MSIM_RNG_REPLAY ? sim_kernel<MSIM_POLICY_EDD, MSIM_RNG_REPLAY>
+                                      : sim_kernel<MSIM_POLICY_EDD, MSIM_RNG_PHILOX>;
     return nullptr;
 }
 
@@ -938,7 +1212,7 @@ int launch_sim(const KParams& p, int policy, int rng_mode, int grid, int block, 
     sim_fn f = pick(policy, rng_mode);
     if (!f) return MSIM_E_UNSUPPORTED;
     // the opt-in limit is per function, not per handle: several handles with different slab sizes share a kernel
-    static size_t smem_set[3][2] = {{0, 0}, {0, 0}, {0, 0}};
+    static size_t smem_set[4][2] = {{0, 0}, {0, 0}, {0, 0}, {0, 0}};
     if (smem > smem_set[policy][rng_mode]) {
         if (cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return MSIM_E_CUDA;
         smem_set[policy][rng_mode] = smem;

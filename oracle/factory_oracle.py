@@ -72,7 +72,7 @@ class _DO:
 
 
 class FactoryOracle:
-    """One replication.  ``policy`` in {"fifo", "max_priority", "dbr"}; ``variates`` is None (reference
+    """One replication.  ``policy`` in {"fifo", "max_priority", "dbr", "edd"}; ``variates`` is None (reference
     generators seeded with ``seed``) or a dict of ``TapeSource`` objects {"A","B","D"} (B carries tape C too)."""
 
     def __init__(self, config, resources, products, seed=None, policy="fifo", variates=None,
@@ -262,6 +262,8 @@ class FactoryOracle:
             return po
         if self.policy == "max_priority":
             pick = max(items, key=lambda o: o.prio)
+        elif self.policy == "edd":     # extension (not in the reference): earliest due date, FIFO among equals
+            pick = min(items, key=lambda o: o.due)
         else:  # dbr buffer-penetration dispatch, toc_dbr/simulation.py:291-328
             for o in items:
                 ahead = []

@@ -78,6 +78,14 @@ def scenario_table():
     out["dbr_shipped"] = dict(cfg=sim, resources=res, products=prod, policy="dbr", seed=54907, patches=["P2"])
     out["dbr_repaired"] = dict(cfg=dict(sim), resources=res, products=prod, policy="dbr", seed=54907,
                                patches=["P2", "P3"])
+    # python-typed clock excursions: zero setups on every other resource make non-CCR orders
+    # released at int-typed tick instants start processing with an int clock + float batch time -> float64 instants
+    res_t = copy.deepcopy(res)
+    for i, r in enumerate(res_t.values()):
+        if i % 2 == 0:
+            r["setup"] = {"dist": "constant", "params": [0, 0]}
+    sim_t = dict(sim, run_until=2501, warmup=400, scheduler_interval=24, cb_target_level=120)
+    out["dbr_typed"] = dict(cfg=sim_t, resources=res_t, products=prod, policy="dbr", seed=91421, patches=["P2", "P3"])
     return out
 
 

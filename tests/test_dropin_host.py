@@ -1,0 +1,113 @@
+"""CPU: host-side drop-in surface -- Logger view semantics (ring wrap quirk E2), hook policing, run-seed derivation,
+shard bounds, moments -> statistics."""
+import numpy as np
+import pandas as pd
+import pytest
+
+from manusim_b200 import compile_scenario, scenarios
+from manusim_b200.experiment import generate_run_seeds, shard_bounds, stats_from_moments
+from manusim_b200.logs import Logger
+from manusim_b200.metrics import (MetricGeneral, MetricProducts, MetricResources, complete_wide_metrics_df,
+                                  frames_from_values, metric_values)
+
+
+def _tables():
+    cfg, res, prod = scenarios.toy2()
+    return compile_scenario(cfg, res, prod)
+
+
+@pytest.mark.parametrize("mem,with_path", [(1000, False), (7, False), (7, True), (1, False)])
+def test_load_stream_equals_sequential_log_calls(tmp_path, mem, with_path):
+    """Folding the stream must leave exactly the state successive Logger.log() calls leave (logs.py:44-66)."""
+    t = _tables()
+    names = t.ring_names()
+    rng = np.random.default_rng(3)
+    n = 200
+    ring = rng.integers(0, len(names), size=n).astype(np.uint32)
+    tm = np.sort(rng.random(n).astype(np.float32) * 100)
+    val = rng.random(n).astype(np.float32)
+    a = Logger.for_tables(t, tmp_path / "a" if with_path else None, mem)
+    b = Logger.for_tables(t, tmp_path / "b" if with_path else None, mem)
+    a.load_stream(names, ring, tm, val)
+    for r, x, y in zip(ring, tm, val):
+        b.log(names[r][0], names[r][1], (x, y))
+    for variable, key in names:
+        assert a.log_index[variable][key] == b.log_index[variable][key]
+        assert np.array_equal(getattr(a, variable)[key], getattr(b, variable)[key]), (variable, key)
+        if with_path:
+            fa, fb = tmp_path / "a" / f"log_{variable}_{key}.csv", tmp_path / "b" / f"log_{variable}_{key}.csv"
+            assert fa.exists() == fb.exists()
+            if fa.exists():
+                pd.testing.assert_frame_equal(pd.read_csv(fa), pd.read_csv(fb))
+    assert a.get_last_log_value(*names[int(ring[-1])]) == b.get_last_log_value(*names[int(ring[-1])])
+
+
+def test_run_seeds_match_reference():
+    assert generate_run_seeds(123, 5) == [54907, 280679, 91421, 806309, 427023]
+
+
+def test_shard_bounds_partition():
+    for n in (1, 7, 1000, 8_000_000):
+        for w in (1, 2, 3, 8):
+            b = [shard_bounds(n, w, r) for r in range(w)]
+            assert b[0][0] == 0 and b[-1][1] == n
+            assert all(b[i][1] == b[i + 1][0] for i in range(w - 1))
+
+
+def test_stats_from_moments():
+    x = np.array([1.0, 2.0, 4.0])
+    mom = np.array([[x.sum(), (x * x).sum(), 3.0], [0.0, 0.0, 0.0]])
+    st = stats_from_moments(mom)
+    assert st["mean"][0] == pytest.approx(x.mean()) and st["std"][0] == pytest.approx(x.std(ddof=1))
+    assert np.isnan(st["mean"][1])
+
+
+def test_metric_values_and_frames():
+    t = _tables()
+    K = t.n_rings
+    s = np.arange(K, dtype=np.float64) + 1
+    c = np.ones(K, dtype=np.int64) * 2
+    c[3] = 0
+    v = metric_values(s, c, t, span=10.0)
+    P, R = t.P, t.R
+    assert v[0] == 1.0                         # deliveredOntime: sum
+    assert np.isnan(v[3])                      # flowTime: mean of nothing
+    assert v[11 * P] == s[11 * P] / 10.0       # utilization: sum / span
+    assert v[4] == s[4] / 2
+    prod, res, gen = frames_from_values(v, t)
+    assert list(prod.columns) == ["key"] + [m.name for m in MetricProducts]
+    assert list(res.columns) == ["key"] + [m.name for m in MetricResources]
+    assert list(gen.columns) == ["key"] + [m.name for m in MetricGeneral]
+
+
+def test_complete_wide_fill_rules():
+    df = pd.DataFrame({"utilization": [0.5]}, index=pd.Index(["rA"], name="key"))
+    out = complete_wide_metrics_df(df, list(MetricResources), ["rA", "rB"])
+    assert out.loc[1, "utilization"] == 0.0 and out.loc[1, "breakdown"] == 0.0 and np.isnan(out.loc[1, "queue"])
+
+
+def test_unknown_hook_override_is_refused():
+    from manusim_b200.factory_sim import DBRSimulation, FactorySimulation, NewSimulation
+
+    cfg, res, prod = scenarios.toy2()
+
+    class Custom(FactorySimulation):
+        def order_selection(self, resource):
+            yield None
+
+    with pytest.raises(NotImplementedError, match="recognised policies"):
+        Custom(cfg, res, prod)
+
+    class Custom2(NewSimulation):
+        def _custom_fg_reduced(self, product):
+            print("x")
+
+    with pytest.raises(NotImplementedError):
+        Custom2(cfg, res, prod)
+    sim = NewSimulation(cfg, res, prod)                # recognised classes construct on CPU (tables only)
+    assert sim.policy == "max_priority" and sim.logs.log_index["wip"]["p1"] == 0
+    sim2, r2, p2, _ = scenarios.load_example("toc_dbr")
+    d = DBRSimulation(sim2, r2, p2)
+    assert d.contraint_resource == "r09" and d.scheduler_interval == 48
+    with pytest.raises(ValueError, match="run_until must be specified"):
+        FactorySimulation({}, res, prod)

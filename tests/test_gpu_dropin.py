@@ -1,0 +1,182 @@
+"""GPU: the drop-in surface (FactorySimulation / Logger view / metrics DataFrames / batched ExperimentRunner) and the
+sharding invariants, through the public Python API."""
+import json
+
+import numpy as np
+import pandas as pd
+import pytest
+
+from conftest import load_golden
+
+pytestmark = pytest.mark.gpu
+
+
+def _ring_records(g, rid):
+    sel = g["ring"] == rid
+    return np.stack([g["time"][sel], g["value"][sel]], axis=1)
+
+
+def test_factory_simulation_replay_matches_reference_logs_and_metrics():
+    from manusim_b200.factory_sim import NewSimulation
+
+    g = load_golden("ss_cfg1")
+    s = g["scenario"]
+    sim = NewSimulation(s["cfg"], s["resources"], s["products"], print_mode="none")
+    sim.reset_simulation(s["seed"], None, tapes={k: g["tape_" + k] for k in "ABCD"})
+    elapsed = sim.run_simulation()
+    assert elapsed > 0 and sim.seed == s["seed"]
+    assert sim.env.now == 1000 and isinstance(sim.env.now, int)          # run_until stays an int
+    assert sim.sim_events == g["steps"]
+    for rid, (variable, key) in enumerate(sim.tables.ring_names()):
+        want = _ring_records(g, rid)
+        li = sim.logs.log_index[variable][key]
+        assert li == len(want)
+        assert np.array_equal(getattr(sim.logs, variable)[key][:li], want)
+    m = g["metrics"]
+    for fam, df in (("products", sim.products_metrics()), ("resources", sim.resources_metrics()),
+                    ("general", sim.general_metrics())):
+        want = pd.DataFrame(m[fam])
+        assert list(df.columns) == list(want.columns)
+        assert list(df["key"]) == list(want["key"])
+        for col in df.columns[1:]:
+            np.testing.assert_allclose(df[col].to_numpy(dtype=float), want[col].to_numpy(dtype=float), rtol=1e-6,
+                                       equal_nan=True)
+
+
+def test_small_memory_size_reproduces_ring_wrap(tmp_path):
+    """memory_size=100 as shipped (conf/config.yaml:22): visible counts wrap, old rows go to CSV when a path is set."""
+    from manusim_b200.factory_sim import NewSimulation
+
+    g = load_golden("ss_cfg1")
+    s = g["scenario"]
+    cfg = dict(s["cfg"], memory_size=100)
+    sim = NewSimulation(cfg, s["resources"], s["products"], print_mode="none")
+    sim.reset_simulation(s["seed"], tmp_path / "logs", tapes={k: g["tape_" + k] for k in "ABCD"})
+    sim.run_simulation()
+    rid = [i for i, n in enumerate(sim.tables.ring_names()) if n == ("utilization", "r09")][0]
+    want = _ring_records(g, rid)
+    li = sim.logs.log_index["utilization"]["r09"]
+    assert li == (len(want) - 1) % 100 + 1
+    saved = pd.read_csv(tmp_path / "logs" / "log_utilization_r09.csv")
+    assert len(saved) == len(want) - li
+    sim.save_metrics(tmp_path / "run", saved_logs=True)                   # the ExperimentRunner flow (experiment.py:59)
+    got = pd.read_csv(tmp_path / "run" / "metrics_resources.csv")
+    ref = pd.DataFrame(g["metrics"]["resources"])
+    np.testing.assert_allclose(got["utilization"].to_numpy(), ref["utilization"].to_numpy(dtype=float), rtol=1e-5)
+    assert got.columns[0] == "Unnamed: 0"                                 # pandas index column kept (quirk E14)
+
+
+def test_batched_experiment_runner_tree(tmp_path):
+    import yaml
+
+    from manusim_b200 import scenarios
+    from manusim_b200.experiment import ExperimentRunner, generate_run_seeds
+    from manusim_b200.factory_sim import NewSimulation
+
+    sim_cfg, res, prod, exp = scenarios.load_example("simple_scheduler")
+    cfg = dict(sim_cfg, run_until=300, memory_size=5000)
+    sim = NewSimulation(cfg, res, prod, print_mode="none")
+    runner = ExperimentRunner(sim, number_of_runs=6, save_folder_path=tmp_path, run_name="t", save_logs=True,
+                              seed=exp["exp_seed"])
+    metas = runner.run_experiment()
+    seeds = generate_run_seeds(exp["exp_seed"], 6)
+    assert [m["seed"] for m in metas] == seeds
+    for i in range(1, 7):
+        rf = tmp_path / f"run_{i:03d}"
+        for f in ("metrics_products.csv", "metrics_resources.csv", "metrics_general.csv", "run_info.yaml"):
+            assert (rf / f).exists()
+        info = yaml.safe_load((rf / "run_info.yaml").read_text())
+        assert set(info) == {"run_id", "seed", "elapsed_time", "simulation_end_time", "run_folder"}
+        assert info["simulation_end_time"] == 300
+        assert (rf / "logs" / "log_utilization_r01.csv").exists()
+        lg = pd.read_csv(rf / "logs" / "log_utilization_r01.csv")
+        assert list(lg.columns) == ["time", "value", "variable", "key"]
+        mr = pd.read_csv(rf / "metrics_resources.csv")
+        np.testing.assert_allclose(mr["utilization"][0], lg["value"].sum() / (300 - 50), rtol=1e-6)
+    assert (tmp_path / "experiment_summary.yaml").exists() and (tmp_path / "experiment_metadata.csv").exists()
+    st = pd.read_csv(tmp_path / "experiment_stats_device.csv")
+    u = [pd.read_csv(tmp_path / f"run_{i:03d}" / "metrics_resources.csv")["utilization"][0] for i in range(1, 7)]
+    row = st[(st.variable == "utilization") & (st.key == "r01")].iloc[0]
+    assert row["size"] == 6
+    np.testing.assert_allclose(row["mean"], np.mean(u), rtol=1e-9)
+    np.testing.assert_allclose(row["std"], np.std(u, ddof=1), rtol=1e-6)
+
+
+def test_results_are_shard_invariant():
+    """Replication i gives identical bits whether it runs in one 96-replication launch or in shards with rep_offset
+    (keys are a function of the GLOBAL index); moments add up exactly like a single-GPU run."""
+    import torch
+
+    from manusim_b200 import BatchEngine, compile_scenario, scenarios
+
+    cfg, res, prod = scenarios.jobshop20(run_until=400, warmup=50)
+    eng = BatchEngine(compile_scenario(cfg, res, prod))
+    full = eng.run(96, seed=5)
+    a = eng.run(40, seed=5, rep_offset=0)
+    b = eng.run(56, seed=5, rep_offset=40)
+    torch.cuda.synchronize()
+    for f in ("acc_sum", "acc_cnt", "n_events", "status"):
+        assert torch.equal(getattr(full, f), torch.cat([getattr(a, f), getattr(b, f)])), f
+    m_full = eng.reduce(full)
+    m_parts = eng.reduce(a)
+    eng.reduce(b, out=m_parts)
+    torch.cuda.synchronize()
+    np.testing.assert_allclose(m_full.cpu().numpy(), m_parts.cpu().numpy(), rtol=1e-12)
+    assert m_full[0, 2].item() == 96
+
+
+def test_host_buffer_path_equals_device_path():
+    import torch
+
+    from manusim_b200 import BatchEngine, compile_scenario, scenarios
+
+    cfg, res, prod = scenarios.jobshop20(run_until=300, warmup=50, mode="onDue")
+    eng = BatchEngine(compile_scenario(cfg, res, prod))
+    d = eng.run(33, seed=9)
+    h = eng.run_host(33, seed=9)
+    torch.cuda.synchronize()
+    assert h.kernel_ms > 0
+    assert torch.equal(d.acc_sum.cpu(), h.acc_sum) and torch.equal(d.acc_cnt.cpu(), h.acc_cnt)
+    assert torch.equal(d.n_events.cpu(), h.n_events) and torch.equal(d.status.cpu(), h.status)
+
+
+def test_philox_statistics_agree_with_reference_generators():
+    """Philox mode vs the reference's MT19937/PCG64 generators: per-metric means over replications must agree within
+    4.5 standard errors (two-sample z, Bonferroni-safe for ~60 metrics)."""
+    import torch
+
+    from manusim_b200 import BatchEngine, compile_scenario, scenarios
+    from manusim_b200.metrics import metric_values
+    from oracle.factory_oracle import metrics_from_trace, run_oracle
+    from oracle.variates import run_seeds
+
+    sim_cfg, res, prod, _ = scenarios.load_example("simple_scheduler")
+    cfg = dict(sim_cfg, run_until=400, warmup=50)
+    t = compile_scenario(cfg, res, prod, policy="max_priority")
+    n_cpu, n_gpu = 48, 4096
+    cpu = []
+    for seed in run_seeds(777, n_cpu):
+        o = run_oracle(cfg, res, prod, seed, "max_priority")
+        cpu.append(metrics_from_trace(o, t.P, t.R, 400, 50)[2])
+    cpu = np.array(cpu)
+    eng = BatchEngine(t)
+    r = eng.run(n_gpu, seed=2024)
+    torch.cuda.synchronize()
+    assert (r.status.cpu().numpy() == 0).all()
+    gpu = metric_values(r.acc_sum.cpu().numpy(), r.acc_cnt.cpu().numpy(), t, 350.0)
+    names = t.ring_names()
+    checked = 0
+    for k, (variable, key) in enumerate(names):
+        if variable in ("queue", "breakdown", "lostSales", "setup"):
+            continue
+        a, b = cpu[:, k], gpu[:, k]
+        a, b = a[~np.isnan(a)], b[~np.isnan(b)]
+        if len(a) < n_cpu // 2 or len(b) < n_gpu // 2:
+            continue
+        # under H0 both samples share one distribution: use the large (GPU) sample's variance for both terms, so that
+        # rare-event metrics whose 48 CPU replications are all zero do not get a zero standard error
+        v = max(a.var(ddof=1), b.var(ddof=1))
+        se = np.sqrt(v / len(a) + v / len(b))
+        assert abs(a.mean() - b.mean()) <= 4.5 * se + 1e-9, (variable, key, a.mean(), b.mean(), se)
+        checked += 1
+    assert checked > 100

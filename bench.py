@@ -45,6 +45,7 @@ def workload_spec(name, run_until=None):
         a = scenarios.jobshop20(run_until=ru, warmup=wu, mode="asReady")
         b = scenarios.jobshop20(run_until=ru, warmup=wu, mode="onDue")
         return {"name": name, "parts": [(a, "fifo", 0, 2), (b, "fifo", 1, 2)], "run_until": ru, "warmup": wu,
+                "pools": [(0, 0), (0, 160)],     # (production-order, demand-order) pool sizes; onDue keeps orders until due
                 "desc": f"jobshop20 (BASELINE config #4: R=20,P=10, setups, TBF/TTR breakdowns, even=asReady/odd=onDue, "
                         f"run_until={ru}, warmup={wu})"}
     if name == "simple_det":
@@ -222,9 +223,10 @@ def main():
 
     spec = workload_spec(args.workload, args.run_until)
     parts = []
-    for (cfg, res, prod), policy, phase, period in spec["parts"]:
-        eng = BatchEngine(compile_scenario(cfg, res, prod, policy=policy, max_production_orders=args.max_po,
-                                           max_demand_orders=args.max_do))
+    for i, ((cfg, res, prod), policy, phase, period) in enumerate(spec["parts"]):
+        mpo, mdo = spec.get("pools", [(0, 0)] * len(spec["parts"]))[i]
+        eng = BatchEngine(compile_scenario(cfg, res, prod, policy=policy, max_production_orders=args.max_po or mpo,
+                                           max_demand_orders=args.max_do or mdo))
         n = args.reps // period
         parts.append({"eng": eng, "n": n, "phase": phase, "period": period})
     K = parts[0]["eng"].K
@@ -238,6 +240,7 @@ def main():
     stats = torch.zeros((K, 3), dtype=torch.float64, device=dev)
     ev_total = torch.zeros((), dtype=torch.int64, device=dev)
     fail_total = torch.zeros((), dtype=torch.int64, device=dev)
+    fail_codes = torch.zeros((9,), dtype=torch.int64, device=dev)
     rec_total = torch.zeros((), dtype=torch.int64, device=dev)
     flush_buf = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)   # > 126 MB L2
     stream = torch.cuda.current_stream(dev)
@@ -270,6 +273,7 @@ def main():
                 ev_total.add_(p["res"].n_events.sum())
                 rec_total.add_(p["res"].acc_cnt.sum(dtype=torch.int64))
                 fail_total.add_((p["res"].status != 0).sum())
+                fail_codes.add_(torch.bincount(p["res"].status, minlength=9)[:9])
 
     for w in range(args.warmup):
         device_step(w, False)
@@ -365,6 +369,7 @@ def main():
             "e2e": {"value": e2e_value, "unit": "events/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
             "gpu_launches": (2 * len(parts)) * args.steps,
             "failed_replications": int(fail_total.item()),
+            "status_histogram": fail_codes.tolist(),
             "engine": {k: parts[0]["eng"].info[k] for k in ("smem_per_replication", "warps_per_block", "blocks_per_sm",
                                                              "regs_per_thread", "n_sms")},
             "roofline": roofline}

@@ -199,6 +199,7 @@ def main():
     ap.add_argument("--cpu-workers", type=int, default=0)
     ap.add_argument("--max-po", type=int, default=0, help="production-order pool per replication (0 = library default)")
     ap.add_argument("--max-do", type=int, default=0, help="demand-order pool per replication (0 = library default)")
+    ap.add_argument("--fifo", type=int, default=0, help="zero-delay event ring capacity (0 = library default)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
@@ -226,7 +227,7 @@ def main():
     for i, ((cfg, res, prod), policy, phase, period) in enumerate(spec["parts"]):
         mpo, mdo = spec.get("pools", [(0, 0)] * len(spec["parts"]))[i]
         eng = BatchEngine(compile_scenario(cfg, res, prod, policy=policy, max_production_orders=args.max_po or mpo,
-                                           max_demand_orders=args.max_do or mdo))
+                                           max_demand_orders=args.max_do or mdo, fifo_capacity=args.fifo))
         n = args.reps // period
         parts.append({"eng": eng, "n": n, "phase": phase, "period": period})
     K = parts[0]["eng"].K

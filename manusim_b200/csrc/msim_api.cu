@@ -47,8 +47,16 @@ static DDist to_ddist(const msim_dist_t& d) {
     o.pad = 0;
     o.d0 = (float)d.d0;
     o.d1 = (float)d.d1;
+    o.mt_d = 0.f; o.mt_c = 0.f;
+    if (d.kind == MSIM_DIST_GAMMA || d.kind == MSIM_DIST_ERLANG) {
+        float k = o.d0;
+        float kk = k < 1.0f ? k + 1.0f : k;
+        o.mt_d = kk - (1.0f / 3.0f);
+        o.mt_c = 1.0f / sqrtf(9.0f * o.mt_d);
+    }
     return o;
 }
+DDist msim::make_ddist(const msim_dist_t& d) { return to_ddist(d); }
 
 static const char* check_dist(const msim_dist_t& d, bool allow_none) {
     if (d.kind == MSIM_DIST_NONE) return allow_none ? nullptr : "missing distribution";
@@ -105,7 +113,7 @@ extern "C" int msim_create(const msim_tables_t* t, msim_handle_t* out) {
     L.NT = align_up(R + P + 2, 32);
     L.MP = t->max_production_orders > 0 ? t->max_production_orders : 96;
     L.MD = t->max_demand_orders > 0 ? t->max_demand_orders : 96;
-    L.NQ = t->fifo_capacity > 0 ? t->fifo_capacity : 64;
+    L.NQ = t->fifo_capacity > 0 ? t->fifo_capacity : 128;   // every live process owns at most one pending zero-delay event
     L.UQ = t->policy == MSIM_POLICY_DBR ? 64 : 16;          // a rope tick spawns up to P process_order Initialize events
     if (L.MP > 250 || L.MD > 250 || (L.NQ & (L.NQ - 1))) { delete h; return fail(MSIM_E_INVALID, "bad pool capacities"); }
     L.K = 11 * P + 4 * R + 3;
@@ -121,16 +129,19 @@ extern "C" int msim_create(const msim_tables_t* t, msim_handle_t* out) {
     L.uq = take(L.UQ * 4, 4);
     L.tm_time = take(L.NT * 4, 4);
     L.tm_eid = take(L.NT * 4, 4);
+    L.tm_ev = take(L.NT * 4, 4);
+    L.rb = take(2 * 16 * 8, 8);                 // precomputed (x,u) pairs of streams B,C (philox.cuh kXuBuf)
     L.r_tpy = dbr ? take(R * 8, 8) : 0; L.r_start_d = dbr ? take(R * 8, 8) : 0; L.r_utf_d = dbr ? take(R * 8, 8) : 0;
     L.r_utf = take(R * 4, 4); L.r_tbf = take(R * 4, 4); L.r_setup = take(R * 4, 4); L.r_start = take(R * 4, 4);
-    L.r_busy = take(R * 4, 4); L.r_qq = take(R * 4, 4); L.r_lastq = take(R * 4, 4);
+    L.r_busy = take(R * 4, 4);
+    L.r_qq = t->log_queues ? take(R * 4, 4) : 0; L.r_lastq = t->log_queues ? take(R * 4, 4) : 0;   // `queue` records only
     L.p_fg = take(P * 4, 4); L.p_wip = take(P * 4, 4); L.p_fgc = take(P * 4, 4); L.p_dqty = take(P * 4, 4);
     L.p_ddue = take(P * 4, 4);
     L.po_rel = take(L.MP * 4, 4); L.po_qty = take(L.MP * 4, 4);
     L.po_prio = prio ? take(L.MP * 4, 4) : 0;
     L.po_tt = dbr ? take(L.MP * 4, 4) : 0; L.po_eid = dbr ? take(L.MP * 4, 4) : 0; L.po_ccr = dbr ? take(L.MP * 4, 4) : 0;
     L.do_arr = take(L.MD * 4, 4); L.do_due = take(L.MD * 4, 4); L.do_qty = take(L.MD * 4, 4);
-    L.do_tt = take(L.MD * 4, 4);               // kept for every mode: the calendar scan reads it only for onDue
+    L.do_tt = on_due ? take(L.MD * 4, 4) : 0;  // delivery timers exist only in onDue mode
     L.do_eid = on_due ? take(L.MD * 4, 4) : 0;
     L.r_flags = dbr ? take(R, 1) : 0; L.po_relpy = dbr ? take(L.MP, 1) : 0;
     L.r_phase = take(R, 1); L.r_cur = take(R, 1); L.r_tcur = take(R, 1);
@@ -183,12 +194,25 @@ extern "C" int msim_create(const msim_tables_t* t, msim_handle_t* out) {
         L.t_step_res = put(sr.data(), sr.size(), 1);
         blob.resize((blob.size() + 15) / 16 * 16);
         L.t_bytes = (int)blob.size();
+        if (blob.size() > (size_t)kTabMax) {
+            delete h;
+            return fail(MSIM_E_UNSUPPORTED, "scenario tables exceed the 12 KB kernel-parameter budget (too many route steps)");
+        }
+        memcpy(h->kp.tblob, blob.data(), blob.size());
     }
 
     KParams& kp = h->kp;
     kp.run_until = (float)t->run_until;
     kp.warmup = (float)t->warmup;
     kp.warmup_d = t->warmup;
+    {
+        int m = 0;
+        for (int p = 0; p < P; ++p)
+            if (t->prod_freq[p].kind > 0 || t->prod_qty[p].kind > 0 || t->prod_due[p].kind > 0) m |= 1;
+        for (int r = 0; r < R; ++r) if (t->res_setup[r].kind > 0) m |= 2;
+        for (int s_ = 0; s_ < S; ++s_) if (t->step_time[s_].kind > 0) m |= 4;
+        kp.rng_streams = m;
+    }
     kp.delivery_mode = t->delivery_mode;
     kp.log_queues = t->log_queues ? 1 : 0;
     kp.dbr_ccr = t->dbr_ccr; kp.dbr_repair = t->dbr_repair;
@@ -209,7 +233,7 @@ extern "C" int msim_create(const msim_tables_t* t, msim_handle_t* out) {
     for (int rng = 0; rng < 2; ++rng) {
         int best_w = 0, best_total = 0, best_blocks = 0;
         for (int w = 1; w <= 8; ++w) {
-            size_t need = (size_t)L.t_bytes + (size_t)w * L.slab_bytes;
+            size_t need = (size_t)w * L.slab_bytes;
             if (need > smem_blk_max) break;
             int nblk = 0, regs = 0;
             int rc = sim_kernel_attrs(h->policy, rng, need, &regs, w * 32, &nblk);
@@ -224,7 +248,7 @@ extern "C" int msim_create(const msim_tables_t* t, msim_handle_t* out) {
         if (best_total == 0) { delete h; return fail(MSIM_E_UNSUPPORTED, "scenario does not fit shared memory"); }
         h->warps_per_block[rng] = best_w;
         h->blocks_per_sm[rng] = best_blocks;
-        h->smem_bytes[rng] = (size_t)L.t_bytes + (size_t)best_w * L.slab_bytes;
+        h->smem_bytes[rng] = (size_t)best_w * L.slab_bytes;
     }
     if (cudaMalloc(&h->d_tables, blob.size()) != cudaSuccess || cudaMalloc(&h->d_counter, 8) != cudaSuccess) {
         delete h;

@@ -9,12 +9,14 @@ constexpr int kWarp = 32;
 constexpr int kStageCap = 32;      // staged records per replication (one 128-bit record per lane on flush)
 constexpr int kStageFlushAt = 25;  // a single event emits at most 7 records
 constexpr uint32_t kNone = 0xFFu;
+constexpr int kTabMax = 12288;     // scenario tables travel in the kernel parameters (constant bank), not shared memory
 
 // device-side distribution entry (block-shared table)
 struct DDist {
     double raw0;   // params[0] in float64 (constant batch = count * raw0, utils.py:83-84)
     float d0, d1;  // derived parameters rounded to float32 for the Philox samplers
     int32_t kind;
+    float mt_d, mt_c;  // gamma/erlang: Marsaglia-Tsang d = k' - 1/3, c = 1/sqrt(9 d) with k' = k < 1 ? k + 1 : k
     int32_t pad;
 };
 
@@ -30,6 +32,7 @@ struct Scal {
     uint32_t tlen[4];       // replay: tape lengths
     const void* tbase[4];   // replay: tape base pointers of this replication
     uint32_t k0, k1;        // Philox replication key
+    uint32_t rb_base[3];    // draw index held by slot 0 of the precomputed (x,u) buffer of streams A,B,C
     uint32_t n_timeouts;
     uint8_t sched_wait;     // scheduler blocked on inbound.get()
     uint8_t inb_head, inb_tail;   // inbound_demand_orders items (linked through do_next)
@@ -49,7 +52,7 @@ struct Scal {
 struct Lay {
     int32_t R, P, S, NT, MP, MD, NQ, UQ, K;
     // per-replication slab
-    int32_t stage, nq, uq, tm_time, tm_eid;
+    int32_t stage, nq, uq, tm_time, tm_eid, tm_ev, rb;
     int32_t r_utf, r_tbf, r_setup, r_start, r_busy, r_qq, r_lastq;
     int32_t p_fg, p_wip, p_fgc, p_dqty, p_ddue;
     int32_t po_rel, po_qty, po_prio, po_tt, po_eid, po_ccr;
@@ -65,8 +68,9 @@ struct Lay {
 };
 
 struct KParams {
+    alignas(16) unsigned char tblob[kTabMax];   // scenario tables (routes, distributions): read with LDC, cost no shared memory
     Lay lay;
-    const unsigned char* tables;   // device copy of the table blob (t_bytes)
+    const unsigned char* tables;   // unused (kept for ABI stability of the struct)
     unsigned long long* work_counter;
     float run_until, warmup;       // float32 views (heap comparisons happen at float32 precision, Appendix B.1)
     int32_t delivery_mode, log_queues;
@@ -74,7 +78,7 @@ struct KParams {
     int32_t dbr_ccr, dbr_repair;
     double dbr_interval, dbr_cb_target, dbr_release_limit, dbr_ccr_limit, dbr_min_lot, dbr_ccr_setup;
     double warmup_d;               // exact (python-typed) warm-up instant
-    int32_t warps_per_block, _pad;
+    int32_t warps_per_block, rng_streams;   // bit s: stream s (A,B,C) has at least one non-constant distribution
     msim_run_args_t a;             // device pointers
 };
 
@@ -85,5 +89,6 @@ int launch_reduce(const double* acc_sum, const uint32_t* acc_cnt, const int32_t*
                   int R, double span, double* out, void* stream);
 int launch_test_philox(const uint32_t* ctr, const uint32_t* key, uint32_t* out, int64_t n);
 int launch_test_variates(DDist d, uint64_t seed, int stream_id, int batch_count, double* out, int64_t n);
+DDist make_ddist(const msim_dist_t& d);
 
 } // namespace msim

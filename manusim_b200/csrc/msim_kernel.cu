@@ -46,6 +46,8 @@ enum Op : uint32_t {
 enum Phase : uint8_t { PH_SETUP = 0, PH_PROC = 1, PH_TTR = 2 };
 enum Loc : uint8_t { LOC_NONE = 0, LOC_IN = 1, LOC_PROC = 2, LOC_OUT = 3, LOC_TRANS = 4 };
 enum Req : int { REQ_ADVANCE = 0, REQ_FLUSH = 1, REQ_DONE = 2, REQ_SELECT = 3 };
+// lane 0 "attention" bits: the fast path of the event loop (pop NORMAL fifo, dispatch) runs while this word is zero
+enum { A_PENDING = 1, A_URGENT = 2, A_SAME = 4, A_FLUSH = 8, A_STATUS = 16, A_SELECT = 32 };
 // DBR per-resource flags: python-typed (int / float64) values of the dynamically typed clock (Appendix B.2)
 enum { F_TIMER_PY = 1, F_START_PY = 2, F_UTF_PY = 4 };
 
@@ -64,6 +66,43 @@ __device__ __forceinline__ float round3(float x) { return __fdiv_rn(rintf(__fmul
 // within one ulp of a half-way point (documented deviation)
 __device__ __forceinline__ double pyround6(double x) { return __ddiv_rn(rint(__dmul_rn(x, 1e6)), 1e6); }
 
+// Slow path of a Philox-mode draw, one out-of-line copy per kernel: used by the cold call sites (boot, breakdowns,
+// demand triplets) and as the fallback of the inlined fast paths (buffer miss, Marsaglia-Tsang squeeze failure,
+// shape < 1, batches of more than one sample, tape recording).  Bumps the stream's draw index itself.
+// count < 0: scalar draw (DistributionGenerator.random_number, clamped at 0); count >= 0: batch sum.
+__device__ __noinline__ double philox_draw_slow(const KParams& p, Scal* sc, const float2* rb, long long rep, int stream,
+                                                const DDist* d, int count) {
+    const uint32_t idx = sc->draw[stream]++;
+    double out;
+    if (d->kind == MSIM_DIST_CONSTANT || count == 0) {
+        out = count < 0 ? (double)(d->d0 > 0.0f ? d->d0 : 0.0f) : (double)count * d->raw0;
+    } else {
+        XU r;
+        const bool buffered = stream == 1 || stream == 2;      // only the per-operation streams are precomputed
+        uint32_t off = buffered ? idx - sc->rb_base[buffered ? stream : 1] : 0xFFFFFFFFu;
+        if (off < (uint32_t)kXuBuf) {
+            float2 v = rb[(stream - 1) * kXuBuf + off];
+            r.x = v.x; r.u = v.y;
+        } else {
+            r = raw_xu(sc->k0, sc->k1, (uint32_t)stream, idx, 0u);
+        }
+        PhiloxStream s{sc->k0, sc->k1, (uint32_t)stream, idx};
+        float v;
+        if (count > 1) {
+            v = batch_many(s, d->kind, d->d0, d->d1, count, r);
+        } else {
+            v = sample_from_xu(s, d->kind, d->d0, d->d1, d->mt_d, d->mt_c, r);
+            if ((count < 0 || d->kind == MSIM_DIST_NORMAL) && !(v > 0.0f)) v = 0.0f;   // utils.py:67 / :97-98
+        }
+        out = (double)v;
+    }
+    if (p.a.rec_cap > 0 && (long long)idx < p.a.rec_cap) {
+        if (stream == 2) p.a.rec_C[rep * p.a.rec_cap + idx] = out;
+        else (stream == 0 ? p.a.rec_A : (stream == 1 ? p.a.rec_B : p.a.rec_D))[rep * p.a.rec_cap + idx] = (float)out;
+    }
+    return out;
+}
+
 template <int POLICY, int RNG>
 struct Sim {
     const KParams& p;
@@ -79,6 +118,8 @@ struct Sim {
     uint32_t nev, tseq, same_left;
     int status;
     uint32_t pending;
+    uint32_t attn;
+    uint32_t rb_need;         // bit s: the precomputed (x,u) buffer of stream s is (nearly) used up
     // DBR only: exact python-typed clock (now is its float32 view) and the pending cooperative dispatch request
     double now_d;
     uint32_t now_py;
@@ -90,11 +131,13 @@ struct Sim {
         : p(p_), sb(sb_), tb(tb_) { sc = reinterpret_cast<Scal*>(sb + p.lay.scal); }
 
 #define ARR(T, field) (reinterpret_cast<T*>(sb + p.lay.field))
-#define TAB(T, field) (reinterpret_cast<const T*>(tb + p.lay.field))
+#define TAB(T, field) (reinterpret_cast<const T*>(p.tblob + p.lay.field))
 
     __device__ __forceinline__ int ringP(int m, int prod) const { return m * p.lay.P + prod; }
     __device__ __forceinline__ int ringR(int m, int r) const { return 11 * p.lay.P + m * p.lay.R + r; }
     __device__ __forceinline__ int ringG(int g) const { return 11 * p.lay.P + 4 * p.lay.R + g; }
+
+    __device__ __forceinline__ void fail(int code) { status = code; attn |= A_STATUS; }
 
     // ------------------------------------------------------------------ event queues
     __device__ __forceinline__ void pushN(uint32_t ev) {
@@ -104,6 +147,8 @@ struct Sim {
     __device__ __forceinline__ void pushU(uint32_t ev) {
         ARR(uint32_t, uq)[uqt & (uint32_t)(p.lay.UQ - 1)] = ev;
         uqt++;
+        attn |= A_URGENT;
+        if (uqt - uqh > (uint32_t)p.lay.UQ) fail(MSIM_ST_FIFO_OVERFLOW);
     }
     // env.timeout(delay) issued by a static process that owns calendar slot `slot`
     __device__ __forceinline__ void timer(int slot, float t, uint32_t ev) {
@@ -112,44 +157,63 @@ struct Sim {
         } else {
             ARR(float, tm_time)[slot] = t;
             ARR(uint32_t, tm_eid)[slot] = tseq++;
+            ARR(uint32_t, tm_ev)[slot] = ev;     // what the calendar hands back when this slot fires
         }
     }
 
     // ------------------------------------------------------------------ variates
-    __device__ __forceinline__ float draw_scalar(int stream, const DDist& d) {
-        uint32_t idx = sc->draw[stream]++;
-        float v;
-        if (RNG == MSIM_RNG_REPLAY) {
-            if (idx >= sc->tlen[stream]) { status = MSIM_ST_TAPE_EXHAUSTED; return 0.0f; }
-            v = __ldg(reinterpret_cast<const float*>(sc->tbase[stream]) + idx);
+    // Inlined fast path shared by the two per-operation draws (setup, processing time): the (x,u) pair is already
+    // in the warp-precomputed buffer and the distribution is normal, or gamma/erlang with shape >= 1 accepted by
+    // the Marsaglia-Tsang squeeze.  Anything else goes to the out-of-line slow path, which yields the same value.
+    __device__ __forceinline__ bool fast_sample(int stream, const DDist& d, float& v) {
+        const uint32_t idx = sc->draw[stream];
+        const uint32_t off = idx - sc->rb_base[stream];
+        if (off >= (uint32_t)kXuBuf - kXuRefillAt) rb_need |= 1u << stream;
+        if (off >= (uint32_t)kXuBuf || p.a.rec_cap > 0) return false;
+        const float2 xu = ARR(float2, rb)[(stream - 1) * kXuBuf + off];
+        if (d.kind == MSIM_DIST_NORMAL) {
+            v = d.d0 + d.d1 * xu.x;
+        } else if ((d.kind == MSIM_DIST_GAMMA || d.kind == MSIM_DIST_ERLANG) && d.d0 >= 1.0f) {
+            const float w = 1.0f + d.mt_c * xu.x;
+            const float x2 = xu.x * xu.x;
+            if (!(w > 0.0f) || !(xu.y < 1.0f - 0.0331f * x2 * x2)) return false;
+            v = d.mt_d * (w * w * w) * d.d1;
         } else {
-            PhiloxStream s{sc->k0, sc->k1, (uint32_t)stream, idx};
-            v = draw_scalar_philox(s, d.kind, d.d0, d.d1);
-            if (p.a.rec_cap > 0 && (long long)idx < p.a.rec_cap) {
-                float* dst = stream == 0 ? p.a.rec_A : (stream == 1 ? p.a.rec_B : p.a.rec_D);
-                dst[rep * p.a.rec_cap + idx] = v;
-            }
+            return false;
         }
-        return v;
+        sc->draw[stream] = idx + 1u;
+        return true;
+    }
+    __device__ __forceinline__ float draw_scalar_hot(int stream, const DDist& d) {
+        if (RNG == MSIM_RNG_REPLAY) return draw_scalar(stream, d);
+        float v;
+        if (fast_sample(stream, d, v)) return v > 0.0f ? v : 0.0f;
+        return (float)philox_draw_slow(p, sc, ARR(float2, rb), rep, stream, &d, -1);
+    }
+    __device__ __forceinline__ float draw_scalar(int stream, const DDist& d) {
+        if (RNG == MSIM_RNG_REPLAY) {
+            uint32_t idx = sc->draw[stream]++;
+            if (idx >= sc->tlen[stream]) { fail(MSIM_ST_TAPE_EXHAUSTED); return 0.0f; }
+            return __ldg(reinterpret_cast<const float*>(sc->tbase[stream]) + idx);
+        }
+        return (float)philox_draw_slow(p, sc, ARR(float2, rb), rep, stream, &d, -1);
     }
     __device__ __forceinline__ double draw_batch(const DDist& d, int count) {
-        uint32_t idx = sc->draw[2]++;
-        double v;
         if (RNG == MSIM_RNG_REPLAY) {
-            if (idx >= sc->tlen[2]) { status = MSIM_ST_TAPE_EXHAUSTED; return 0.0; }
-            v = __ldg(reinterpret_cast<const double*>(sc->tbase[2]) + idx);
-        } else {
-            PhiloxStream s{sc->k0, sc->k1, 2u, idx};
-            v = draw_batch_philox(s, d.kind, d.d0, d.d1, d.raw0, count);
-            if (p.a.rec_cap > 0 && (long long)idx < p.a.rec_cap) p.a.rec_C[rep * p.a.rec_cap + idx] = v;
+            uint32_t idx = sc->draw[2]++;
+            if (idx >= sc->tlen[2]) { fail(MSIM_ST_TAPE_EXHAUSTED); return 0.0; }
+            return __ldg(reinterpret_cast<const double*>(sc->tbase[2]) + idx);
         }
-        return v;
+        float v;
+        if (count == 1 && fast_sample(2, d, v)) return (double)((d.kind == MSIM_DIST_NORMAL && !(v > 0.0f)) ? 0.0f : v);
+        return philox_draw_slow(p, sc, ARR(float2, rb), rep, 2, &d, count < 0 ? 0 : count);
     }
 
     // ------------------------------------------------------------------ records (Logger.log, logs.py:44-66)
     __device__ __forceinline__ void emit(int ring, float t, float v) {
         ARR(uint4, stage)[nstage] = make_uint4(__float_as_uint(t), __float_as_uint(v), (uint32_t)ring, logc + nstage);
         nstage++;
+        if (nstage >= (uint32_t)kStageFlushAt) attn |= A_FLUSH;
     }
     // _log_inventory_metrics, factory_sim.py:551-601 (caller checked warm)
     __device__ __forceinline__ void inventory(int prod, bool with_wip, bool with_fg) {
@@ -201,7 +265,7 @@ struct Sim {
     // ------------------------------------------------------------------ pools and stores
     __device__ __forceinline__ uint32_t alloc_po() {
         uint32_t i = sc->po_free;
-        if (i == kNone) { status = MSIM_ST_PO_POOL_OVERFLOW; return 0; }
+        if (i == kNone) { fail(MSIM_ST_PO_POOL_OVERFLOW); return 0; }
         sc->po_free = ARR(uint8_t, po_next)[i];
         if (DBR) ARR(float, po_tt)[i] = CUDART_INF_F;
         return i;
@@ -213,7 +277,7 @@ struct Sim {
     }
     __device__ __forceinline__ uint32_t alloc_do() {
         uint32_t i = sc->do_free;
-        if (i == kNone) { status = MSIM_ST_DO_POOL_OVERFLOW; return 0; }
+        if (i == kNone) { fail(MSIM_ST_DO_POOL_OVERFLOW); return 0; }
         sc->do_free = ARR(uint8_t, do_next)[i];
         return i;
     }
@@ -256,7 +320,7 @@ struct Sim {
     }
     // finished_goods[prod].get(quantity) issued by a delivery process (ContainerGet.__init__)
     __device__ __forceinline__ void fg_get(int d, int prod) {
-        if (!(ARR(float, do_qty)[d] > 0.0f)) { status = MSIM_ST_AMOUNT_NONPOSITIVE; return; }
+        if (!(ARR(float, do_qty)[d] > 0.0f)) { fail(MSIM_ST_AMOUNT_NONPOSITIVE); return; }
         list_append(ARR(uint8_t, p_fgqh) + prod, ARR(uint8_t, p_fgqt) + prod, ARR(uint8_t, do_next), d);
         serve_fg(prod);
     }
@@ -316,7 +380,7 @@ struct Sim {
         if (DBR) {
             // buffer-penetration dispatch (toc_dbr/simulation.py:291-328) needs a scan of every in-flight order:
             // a single queued order is trivially the minimum, otherwise the whole warp computes the priorities
-            if (ARR(uint8_t, po_next)[h] != kNone) { sel_req = (uint32_t)r + 1u; return; }
+            if (ARR(uint8_t, po_next)[h] != kNone) { sel_req = (uint32_t)r + 1u; attn |= A_SELECT; return; }
             list_pop(ARR(uint8_t, r_inh) + r, ARR(uint8_t, r_int) + r, ARR(uint8_t, po_next));
         } else if (PRIO) {
             // max(orders, key=priority): first maximum in queue order (simple_scheduler/simulation.py:36)
@@ -345,7 +409,6 @@ struct Sim {
         if (ARR(float, r_utf)[r] >= ARR(float, r_tbf)[r]) {
             ARR(float, r_start)[r] = now;                                  // breakdown_start, :272
             float ttr = draw_scalar(3, TAB(DDist, t_ttr)[r]);              // :275
-            ARR(uint8_t, r_phase)[r] = PH_TTR;
             if (DBR) ARR(uint8_t, r_flags)[r] &= ~F_TIMER_PY;
             timer(r, __fadd_rn(now, ttr), EV(OP_TO_TTR, r, 0));
             return;
@@ -420,7 +483,7 @@ struct Sim {
         case OP_REL_PUT1: {                                      // :211-212
             serve_mach(a);
             float q = ARR(float, po_qty)[b];
-            if (!(q > 0.0f)) { status = MSIM_ST_AMOUNT_NONPOSITIVE; break; }
+            if (!(q > 0.0f)) { fail(MSIM_ST_AMOUNT_NONPOSITIVE); break; }
             int prod = ARR(uint8_t, po_prod)[b];
             ARR(float, p_wip)[prod] = __fadd_rn(ARR(float, p_wip)[prod], q);
             pushN(EV(OP_REL_PUT2, a, b));
@@ -430,7 +493,7 @@ struct Sim {
             float q = ARR(float, po_qty)[b];
             int prod = ARR(uint8_t, po_prod)[b];
             sc->tot_wip = __fadd_rn(sc->tot_wip, q);
-            ARR(float, r_qq)[a] = __fadd_rn(ARR(float, r_qq)[a], q);
+            if (p.log_queues) ARR(float, r_qq)[a] = __fadd_rn(ARR(float, r_qq)[a], q);
             if (warm) {
                 emit(ringP(PM_RELEASED, prod), now, q);
                 inventory(prod, true, false);
@@ -440,11 +503,13 @@ struct Sim {
             break;
         }
         case OP_MACH_GOT: {                                      // _production_system :380-395
-            float q = ARR(float, po_qty)[b];
-            ARR(float, r_qq)[a] = __fsub_rn(ARR(float, r_qq)[a], q);
-            if (warm && p.log_queues) {
-                emit(ringR(RM_QUEUE, a), now, ARR(float, r_qq)[a]);
-                ARR(float, r_lastq)[a] = ARR(float, r_qq)[a];
+            if (p.log_queues) {
+                float q = ARR(float, po_qty)[b];
+                ARR(float, r_qq)[a] = __fsub_rn(ARR(float, r_qq)[a], q);
+                if (warm) {
+                    emit(ringR(RM_QUEUE, a), now, ARR(float, r_qq)[a]);
+                    ARR(float, r_lastq)[a] = ARR(float, r_qq)[a];
+                }
             }
             ARR(uint8_t, r_cur)[a] = (uint8_t)b;
             ARR(uint8_t, po_loc)[b] = LOC_PROC;
@@ -452,14 +517,13 @@ struct Sim {
             break;
         }
         case OP_MACH_PUTPROC: {                                  // :397-421 (setup drawn on every operation, quirk E1)
-            float setup = draw_scalar(1, TAB(DDist, t_setup)[a]);
+            float setup = draw_scalar_hot(1, TAB(DDist, t_setup)[a]);
             ARR(float, r_setup)[a] = setup;
             if (warm) emit(ringR(RM_SETUP, a), now, setup);
             pushN(EV(OP_MACH_REQ, a, 0));
             break;
         }
         case OP_MACH_REQ:                                        // :423
-            ARR(uint8_t, r_phase)[a] = PH_SETUP;
             if (DBR) ARR(uint8_t, r_flags)[a] &= ~F_TIMER_PY;
             timer(a, __fadd_rn(now, ARR(float, r_setup)[a]), EV(OP_TO_SETUP, a, 0));
             break;
@@ -469,8 +533,7 @@ struct Sim {
             int step = TAB(uint16_t, t_route_start)[prod] + ARR(uint8_t, po_done)[po];
             ARR(float, r_start)[a] = now;
             double total = draw_batch(TAB(DDist, t_step_dist)[step], (int)ARR(float, po_qty)[po]);
-            if (total < 0.0) { status = MSIM_ST_NEGATIVE_DELAY; break; }
-            ARR(uint8_t, r_phase)[a] = PH_PROC;
+            if (total < 0.0) { fail(MSIM_ST_NEGATIVE_DELAY); break; }
             if (DBR) {
                 uint8_t fl = ARR(uint8_t, r_flags)[a] & ~(F_TIMER_PY | F_START_PY);
                 if (now_py) {
@@ -485,6 +548,7 @@ struct Sim {
                         ARR(double, r_tpy)[a] = td;
                         ARR(float, tm_time)[a] = __double2float_rn(td);
                         ARR(uint32_t, tm_eid)[a] = tseq++;
+                        ARR(uint32_t, tm_ev)[a] = EV(OP_TO_PROC, a, 0);
                         ARR(uint8_t, r_flags)[a] = fl | F_TIMER_PY;
                     }
                     break;
@@ -534,7 +598,7 @@ struct Sim {
                 pushN(EV(OP_TRANS_GOT, a, po));
             }
             if (DBR && p.dbr_repair && a == p.dbr_ccr) {        // patch P3: stores.resource_finished[CCR].put(po)
-                if (sc->fin_n < 5) sc->fin[sc->fin_n++] = ARR(uint8_t, r_cur)[a]; else status = MSIM_ST_FIFO_OVERFLOW;
+                if (sc->fin_n < 5) sc->fin[sc->fin_n++] = ARR(uint8_t, r_cur)[a]; else fail(MSIM_ST_FIFO_OVERFLOW);
                 pushN(EV(OP_FIN_PUT, 0, 0));
             }
             if (warm) emit(ringR(RM_UTIL, a), now, ARR(float, r_busy)[a]);
@@ -578,7 +642,7 @@ struct Sim {
                 ARR(float, p_wip)[prod] = __fsub_rn(w, q);
                 pushN(EV(OP_TRANS_WIPGET, a, 0));
             } else {
-                status = MSIM_ST_WIP_GET_BLOCKED;
+                fail(MSIM_ST_WIP_GET_BLOCKED);
             }
             break;
         }
@@ -612,9 +676,11 @@ struct Sim {
         }
         case OP_TRANS_PUTIN: {                                   // :336-358
             serve_mach(b);
-            float q = ARR(float, po_qty)[ARR(uint8_t, r_tcur)[a]];
-            ARR(float, r_qq)[b] = __fadd_rn(ARR(float, r_qq)[b], q);
-            if (warm && p.log_queues) queue_log_add(b, q);
+            if (p.log_queues) {
+                float q = ARR(float, po_qty)[ARR(uint8_t, r_tcur)[a]];
+                ARR(float, r_qq)[b] = __fadd_rn(ARR(float, r_qq)[b], q);
+                if (warm) queue_log_add(b, q);
+            }
             trans_get(a);
             break;
         }
@@ -779,31 +845,35 @@ struct Sim {
         sc->tick_d = nt;
         ARR(float, tm_time)[p.lay.R + p.lay.P + 1] = __double2float_rn(nt);
         ARR(uint32_t, tm_eid)[p.lay.R + p.lay.P + 1] = tseq++;
+        ARR(uint32_t, tm_ev)[p.lay.R + p.lay.P + 1] = EV(OP_TO_TICK, 0, 0);
     }
 
-    // lane 0: run zero-delay events until the warp has to cooperate again
+    // lane 0: run zero-delay events until the warp has to cooperate again.  Order of service at one timestamp
+    // (SURVEY Appendix A.8): URGENT fifo -> calendar entries landing on `now` -> NORMAL fifo.
     __device__ __forceinline__ int drain() {
         for (;;) {
             uint32_t ev;
-            if (pending) {
-                ev = pending;
-                pending = 0;
-            } else if (uqh != uqt) {
-                ev = ARR(uint32_t, uq)[uqh & (uint32_t)(p.lay.UQ - 1)];
-                uqh++;
-            } else if (same_left) {
-                return REQ_ADVANCE;          // calendar entries at `now` precede NORMAL events created at `now`
-            } else if (nqh != nqt) {
+            if (attn) {
+                if (attn & A_STATUS) return REQ_DONE;
+                if (attn & A_SELECT) { attn &= ~A_SELECT; return REQ_SELECT; }
+                if (attn & A_FLUSH) { attn &= ~A_FLUSH; return REQ_FLUSH; }
+                if (attn & A_PENDING) {
+                    ev = pending;
+                    attn &= ~A_PENDING;
+                } else if (attn & A_URGENT) {
+                    ev = ARR(uint32_t, uq)[uqh & (uint32_t)(p.lay.UQ - 1)];
+                    uqh++;
+                    if (uqh == uqt) attn &= ~A_URGENT;
+                } else {
+                    return REQ_ADVANCE;      // A_SAME: calendar entries at `now` precede NORMAL events created at `now`
+                }
+            } else {
+                if (nqh == nqt) return REQ_ADVANCE;
                 ev = ARR(uint32_t, nq)[nqh & (uint32_t)(p.lay.NQ - 1)];
                 nqh++;
-            } else {
-                return REQ_ADVANCE;
             }
             dispatch(ev);
-            if (DBR && sel_req) return status ? REQ_DONE : REQ_SELECT;
-            if (nqt - nqh > (uint32_t)p.lay.NQ || uqt - uqh > (uint32_t)p.lay.UQ) status = MSIM_ST_FIFO_OVERFLOW;
-            if (status) return REQ_DONE;
-            if (nstage >= (uint32_t)kStageFlushAt) return REQ_FLUSH;
+            if (nqt - nqh > (uint32_t)p.lay.NQ) fail(MSIM_ST_FIFO_OVERFLOW);
         }
     }
 
@@ -812,7 +882,7 @@ struct Sim {
     __device__ __forceinline__ void boot() {
         const int R = p.lay.R, P = p.lay.P;
         now = 0.0f; warm = 0; nqh = nqt = uqh = uqt = 0; nstage = 0; logc = 0; nev = 0; tseq = 0; same_left = 0;
-        status = 0; pending = 0;
+        status = 0; pending = 0; attn = 0; rb_need = (uint32_t)p.rng_streams & 6u;
         now_d = 0.0; now_py = 1; sel_req = 0;
         for (int r = 0; r < R; ++r) {                            // _start_resources :248-261 (draws at construction)
             const DDist& tb_ = TAB(DDist, t_tbf)[r];
@@ -838,11 +908,11 @@ struct Sim {
             for (int prod = 0; prod < P; ++prod) {               // Initialize[_update_finished_goods(p)]: FG.put(shipping_buffer)
                 nev++;
                 float sbuf = __double2float_rn(TAB(double, t_shipbuf)[prod]);
-                if (!(sbuf > 0.0f)) { status = MSIM_ST_AMOUNT_NONPOSITIVE; return; }
+                if (!(sbuf > 0.0f)) { fail(MSIM_ST_AMOUNT_NONPOSITIVE); return; }
                 ARR(float, p_fg)[prod] = sbuf;
                 pushN(EV(OP_SEED_PUT, prod, 0));
             }
-            pending = EV(OP_TO_TICK, 0, 0);                      // Initialize[scheduler] (the rope): first tick at t = 0,
+            pending = EV(OP_TO_TICK, 0, 0); attn |= A_PENDING;   // Initialize[scheduler] (the rope): first tick at t = 0,
             return;                                              // counted and executed by dispatch before any NORMAL event
         }
         nev++;                                                   // Initialize[scheduler]
@@ -886,11 +956,7 @@ __global__ void __launch_bounds__(256, 5) sim_kernel(const __grid_constant__ KPa
     const Lay& L = p.lay;
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
-    // block-shared scenario tables
-    for (int i = threadIdx.x; i < L.t_bytes / 4; i += blockDim.x)
-        reinterpret_cast<uint32_t*>(smem)[i] = reinterpret_cast<const uint32_t*>(p.tables)[i];
-    __syncthreads();
-    unsigned char* sb = smem + L.t_bytes + (size_t)warp * L.slab_bytes;
+    unsigned char* sb = smem + (size_t)warp * L.slab_bytes;
     Sim<POLICY, RNG> s(p, sb, smem);
     Scal* sc = s.sc;
     const bool on_due = p.delivery_mode == MSIM_DELIVERY_ON_DUE;
@@ -912,7 +978,7 @@ __global__ void __launch_bounds__(256, 5) sim_kernel(const __grid_constant__ KPa
         for (int i = lane; i < L.NT; i += 32) reinterpret_cast<float*>(sb + L.tm_time)[i] = CUDART_INF_F;
         #pragma unroll 1
         for (int i = lane; i < L.MD; i += 32) {
-            reinterpret_cast<float*>(sb + L.do_tt)[i] = CUDART_INF_F;
+            if (on_due) reinterpret_cast<float*>(sb + L.do_tt)[i] = CUDART_INF_F;
             (sb + L.do_next)[i] = (uint8_t)(i + 1 < L.MD ? i + 1 : kNone);
         }
         #pragma unroll 1
@@ -923,7 +989,7 @@ __global__ void __launch_bounds__(256, 5) sim_kernel(const __grid_constant__ KPa
         #pragma unroll 1
         for (int i = lane; i < L.R; i += 32) {
             (sb + L.r_inh)[i] = kNone; (sb + L.r_int)[i] = kNone; (sb + L.r_outh)[i] = kNone; (sb + L.r_outt)[i] = kNone;
-            reinterpret_cast<float*>(sb + L.r_lastq)[i] = CUDART_NAN_F;
+            if (p.log_queues) reinterpret_cast<float*>(sb + L.r_lastq)[i] = CUDART_NAN_F;
         }
         #pragma unroll 1
         for (int i = lane; i < L.P; i += 32) {
@@ -936,6 +1002,7 @@ __global__ void __launch_bounds__(256, 5) sim_kernel(const __grid_constant__ KPa
         }
         if (lane == 0) {
             sc->inb_head = kNone; sc->inb_tail = kNone; sc->po_free = 0; sc->do_free = 0;
+            sc->rb_base[0] = sc->rb_base[1] = sc->rb_base[2] = 0u - (uint32_t)kXuBuf;   // empty: index 0 is 16 past the base
             if (RNG == MSIM_RNG_REPLAY) {
                 long long oa = p.a.tape_A_off[rep], ob = p.a.tape_B_off[rep], oc = p.a.tape_C_off[rep], od = p.a.tape_D_off[rep];
                 sc->tbase[0] = p.a.tape_A + oa; sc->tlen[0] = (uint32_t)(p.a.tape_A_off[rep + 1] - oa);
@@ -975,7 +1042,7 @@ __global__ void __launch_bounds__(256, 5) sim_kernel(const __grid_constant__ KPa
                 const float* rel = reinterpret_cast<const float*>(sb + L.po_rel);
                 const float* qty = reinterpret_cast<const float*>(sb + L.po_qty);
                 const float* fg = reinterpret_cast<const float*>(sb + L.p_fg);
-                const double* sbuf = reinterpret_cast<const double*>(smem + L.t_shipbuf);
+                const double* sbuf = reinterpret_cast<const double*>(p.tblob + L.t_shipbuf);
                 uint32_t best = kNone, best_prev = kNone, prev = kNone;
                 float best_pr = 0.0f;
 #pragma unroll 1
@@ -1003,82 +1070,93 @@ __global__ void __launch_bounds__(256, 5) sim_kernel(const __grid_constant__ KPa
                 continue;
             }
 
-            // ---- cooperative next-event selection: min over (time, eid) of every calendar slot
-            unsigned long long best = ~0ull;
-            int slot = -1, cnt = 0;
+            // ---- cooperative next-event selection: SimPy's heap order (time, eid) over every calendar slot.
+            // Each lane finds the minimum of its own slots, then three redux.sync reductions give the earliest
+            // time, the smallest eid at that time and the number of entries tied on it.
+            uint32_t bt = 0xFFFFFFFFu, be = 0xFFFFFFFFu;
+            int bslot = -1, leq = 0;
             {
-                const float* tt = reinterpret_cast<const float*>(sb + L.tm_time);
+                const uint32_t* tt = reinterpret_cast<const uint32_t*>(sb + L.tm_time);
                 const uint32_t* te = reinterpret_cast<const uint32_t*>(sb + L.tm_eid);
 #pragma unroll 1
                 for (int i = lane; i < L.NT; i += 32) {
-                    unsigned long long k = ((unsigned long long)__float_as_uint(tt[i]) << 32) | te[i];
-                    uint32_t kt = (uint32_t)(k >> 32), bt = (uint32_t)(best >> 32);
-                    if (kt == bt) cnt++; else if (kt < bt) cnt = 1;
-                    if (k < best) { best = k; slot = i; }
+                    const uint32_t t = tt[i], e = te[i];
+                    if (t < bt) { bt = t; be = e; bslot = i; leq = 1; }
+                    else if (t == bt) { leq++; if (e < be) { be = e; bslot = i; } }
                 }
                 if (on_due) {
-                    const float* dt = reinterpret_cast<const float*>(sb + L.do_tt);
+                    const uint32_t* dt = reinterpret_cast<const uint32_t*>(sb + L.do_tt);
                     const uint32_t* de = reinterpret_cast<const uint32_t*>(sb + L.do_eid);
 #pragma unroll 1
                     for (int i = lane; i < L.MD; i += 32) {
-                        unsigned long long k = ((unsigned long long)__float_as_uint(dt[i]) << 32) | de[i];
-                        uint32_t kt = (uint32_t)(k >> 32), bt = (uint32_t)(best >> 32);
-                        if (kt == bt) cnt++; else if (kt < bt) cnt = 1;
-                        if (k < best) { best = k; slot = L.NT + i; }
+                        const uint32_t t = dt[i], e = de[i];
+                        if (t < bt) { bt = t; be = e; bslot = L.NT + i; leq = 1; }
+                        else if (t == bt) { leq++; if (e < be) { be = e; bslot = L.NT + i; } }
                     }
                 }
                 if (DBR) {
-                    const float* pt = reinterpret_cast<const float*>(sb + L.po_tt);
+                    const uint32_t* pt = reinterpret_cast<const uint32_t*>(sb + L.po_tt);
                     const uint32_t* pe = reinterpret_cast<const uint32_t*>(sb + L.po_eid);
 #pragma unroll 1
                     for (int i = lane; i < L.MP; i += 32) {
-                        unsigned long long k = ((unsigned long long)__float_as_uint(pt[i]) << 32) | pe[i];
-                        uint32_t kt = (uint32_t)(k >> 32), bt = (uint32_t)(best >> 32);
-                        if (kt == bt) cnt++; else if (kt < bt) cnt = 1;
-                        if (k < best) { best = k; slot = L.NT + L.MD + i; }
+                        const uint32_t t = pt[i], e = pe[i];
+                        if (t < bt) { bt = t; be = e; bslot = L.NT + L.MD + i; leq = 1; }
+                        else if (t == bt) { leq++; if (e < be) { be = e; bslot = L.NT + L.MD + i; } }
                     }
                 }
             }
-#pragma unroll
-            for (int off = 16; off > 0; off >>= 1) {
-                unsigned long long ob = __shfl_xor_sync(FULLMASK, best, off);
-                int oc = __shfl_xor_sync(FULLMASK, cnt, off);
-                int os = __shfl_xor_sync(FULLMASK, slot, off);
-                uint32_t ot = (uint32_t)(ob >> 32), bt = (uint32_t)(best >> 32);
-                if (ot == bt) cnt += oc; else if (ot < bt) cnt = oc;
-                if (ob < best) { best = ob; slot = os; }
+            if (RNG == MSIM_RNG_PHILOX) {
+                // ---- opportunistic bulk refill of the precomputed (x,u) pairs: the warp is converged here anyway
+                uint32_t need = __shfl_sync(FULLMASK, s.rb_need, 0);
+                if (need) {
+#pragma unroll 1
+                    for (int st = 1; st < 3; ++st) {
+                        if (!((need >> st) & 1u)) continue;
+                        const uint32_t next = sc->draw[st];
+                        __syncwarp();
+                        if (lane < kXuBuf) {
+                            XU r = raw_xu(sc->k0, sc->k1, (uint32_t)st, next + (uint32_t)lane, 0u);
+                            reinterpret_cast<float2*>(sb + L.rb)[(st - 1) * kXuBuf + lane] = make_float2(r.x, r.u);
+                        }
+                        __syncwarp();
+                        if (lane == 0) sc->rb_base[st] = next;
+                    }
+                    if (lane == 0) s.rb_need = 0;
+                    __syncwarp();
+                }
             }
-            const uint32_t tbits = (uint32_t)(best >> 32);
+            const uint32_t tbits = __reduce_min_sync(FULLMASK, bt);
             if (tbits >= until_bits) break;      // the URGENT stop event at run_until precedes everything at that time
+            const bool mine = bt == tbits;
+            const uint32_t emin = __reduce_min_sync(FULLMASK, mine ? be : 0xFFFFFFFFu);
+            const uint32_t cnt = __reduce_add_sync(FULLMASK, mine ? (uint32_t)leq : 0u);
+            const unsigned who = __ballot_sync(FULLMASK, mine && be == emin);
+            const int slot = __shfl_sync(FULLMASK, bslot, __ffs(who) - 1);
             if (lane == 0) {
-                if (s.same_left == 0) {
-                    s.now = __uint_as_float(tbits);
-                    s.same_left = (uint32_t)cnt - 1u;
+                if (s.attn & A_SAME) {
+                    if (--s.same_left == 0) s.attn &= ~A_SAME;
                 } else {
-                    s.same_left--;
+                    s.now = __uint_as_float(tbits);
+                    s.same_left = cnt - 1u;
+                    if (cnt > 1u) s.attn |= A_SAME;
                 }
                 sc->n_timeouts++;
                 uint32_t ev;
                 if (DBR) s.now_py = 0;     // Environment._now takes the type of the popped entry (Appendix B.2)
-                if (slot < L.R) {
-                    uint8_t ph = (sb + L.r_phase)[slot];
-                    ev = EV(ph == PH_SETUP ? OP_TO_SETUP : (ph == PH_PROC ? OP_TO_PROC : OP_TO_TTR), slot, 0);
+                if (slot < L.NT) {
+                    ev = reinterpret_cast<const uint32_t*>(sb + L.tm_ev)[slot];
                     reinterpret_cast<float*>(sb + L.tm_time)[slot] = CUDART_INF_F;
-                    if (DBR && ((sb + L.r_flags)[slot] & F_TIMER_PY)) {
-                        s.now_py = 1;
-                        s.now_d = reinterpret_cast<const double*>(sb + L.r_tpy)[slot];
-                    }
-                } else if (slot < L.R + L.P) {
-                    ev = EV(OP_TO_DEMAND, slot - L.R, 0);
-                    reinterpret_cast<float*>(sb + L.tm_time)[slot] = CUDART_INF_F;
-                } else if (slot < L.NT) {
-                    reinterpret_cast<float*>(sb + L.tm_time)[slot] = CUDART_INF_F;
-                    if (slot == L.R + L.P) {
-                        ev = EV(OP_TO_WARMUP, 0, 0);
-                        if (DBR) { s.now_py = 1; s.now_d = p.warmup_d; }
-                    } else {
-                        ev = EV(OP_TO_TICK, 0, 0);
-                        if (DBR) { s.now_py = 1; s.now_d = sc->tick_d; }
+                    if (DBR) {
+                        if (slot < L.R) {
+                            if ((sb + L.r_flags)[slot] & F_TIMER_PY) {
+                                s.now_py = 1;
+                                s.now_d = reinterpret_cast<const double*>(sb + L.r_tpy)[slot];
+                            }
+                        } else if (slot == L.R + L.P) {
+                            s.now_py = 1; s.now_d = p.warmup_d;
+                        } else if (slot == L.R + L.P + 1) {
+                            s.now_py = 1; s.now_d = sc->tick_d;
+                        }
                     }
                 } else if (slot < L.NT + L.MD) {
                     int d = slot - L.NT;
@@ -1090,6 +1168,7 @@ __global__ void __launch_bounds__(256, 5) sim_kernel(const __grid_constant__ KPa
                     reinterpret_cast<float*>(sb + L.po_tt)[po] = CUDART_INF_F;
                 }
                 s.pending = ev;
+                s.attn |= A_PENDING;
             }
             __syncwarp();
         }
@@ -1172,8 +1251,24 @@ __global__ void test_variates_kernel(DDist d, uint64_t seed, int stream_id, int 
     long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
     if (i >= n) return;
     PhiloxStream s{(uint32_t)seed, (uint32_t)(seed >> 32), (uint32_t)stream_id, (uint32_t)i};
-    out[i] = batch_count < 0 ? (double)draw_scalar_philox(s, d.kind, d.d0, d.d1)
-                             : draw_batch_philox(s, d.kind, d.d0, d.d1, d.raw0, batch_count);
+    XU r = raw_xu(s.k0, s.k1, s.stream, s.draw, 0u);
+    float v;
+    if (d.kind == MSIM_DIST_CONSTANT) {
+        out[i] = batch_count < 0 ? (double)(d.d0 > 0.f ? d.d0 : 0.f) : (double)(batch_count > 0 ? batch_count : 0) * d.raw0;
+        return;
+    }
+    if (batch_count < 0) {
+        v = sample_from_xu(s, d.kind, d.d0, d.d1, d.mt_d, d.mt_c, r);
+        v = v > 0.0f ? v : 0.0f;
+    } else if (batch_count == 0) {
+        v = 0.0f;
+    } else if (batch_count == 1) {
+        v = sample_from_xu(s, d.kind, d.d0, d.d1, d.mt_d, d.mt_c, r);
+        if (d.kind == MSIM_DIST_NORMAL && !(v > 0.0f)) v = 0.0f;
+    } else {
+        v = batch_many(s, d.kind, d.d0, d.d1, batch_count, r);
+    }
+    out[i] = (double)v;
 }
 
 // ---------------------------------------------------------------------------------------------------------

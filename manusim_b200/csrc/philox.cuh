@@ -39,94 +39,92 @@ struct PhiloxStream {
 };
 
 #ifdef __CUDACC__
+// Every draw index of every stream owns ONE Philox block, turned into a standard normal x (Box-Muller on words
+// 0,1) and an independent uniform u (word 2).  All six distributions are functions of that (x,u) pair, so a draw
+// has the same value whether its pair was precomputed by the whole warp (bulk refill in the kernel's cooperative
+// phase) or generated on the spot by lane 0 (slow path: boot, breakdown stream, buffer miss).
+struct XU { float x, u; };
+constexpr int kXuBuf = 16;          // precomputed pairs per stream and replication
+constexpr uint32_t kXuRefillAt = 4; // refill when this many (or fewer) remain
+
+__device__ __forceinline__ XU xu_from_words(const uint32_t w[4]) {
+    XU r;
+    float m = sqrtf(-2.0f * __logf(u01(w[0])));
+    r.x = m * cospif(2.0f * u01(w[1]));
+    r.u = u01(w[2]);
+    return r;
+}
+
 // one out-of-line copy per kernel: the simulation kernel is instruction-cache bound, not ALU bound
-__device__ __noinline__ void philox_nl(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1,
-                                       uint32_t out[4]) {
-    philox4x32_10(c0, c1, c2, c3, k0, k1, out);
-}
-
-__device__ __forceinline__ float normal01(const uint32_t w[4]) {
-    // Box-Muller on two of the four words
-    float r = sqrtf(-2.0f * __logf(u01(w[0])));
-    return r * cospif(2.0f * u01(w[1]));
-}
-
-// Marsaglia-Tsang; iteration index is part of the counter so rejections stay reproducible
-__device__ __noinline__ float gamma_mt(const PhiloxStream s, float k, float theta) {
-    float boost = 1.0f;
-    float kk = k;
+__device__ __noinline__ XU raw_xu(uint32_t k0, uint32_t k1, uint32_t stream, uint32_t draw, uint32_t it) {
     uint32_t w[4];
-    if (k < 1.0f) {
-        philox_nl(s.draw, s.stream, 0xFFFFu, 1u, s.k0, s.k1, w);
-        boost = __powf(u01(w[0]), 1.0f / k);
-        kk = k + 1.0f;
-    }
-    const float d = kk - (1.0f / 3.0f);
-    const float c = rsqrtf(9.0f * d);
+    philox4x32_10(draw, stream, it, 0u, k0, k1, w);
+    return xu_from_words(w);
+}
+
+// gamma shape < 1: Gamma(k) = Gamma(k+1) * U^(1/k)
+__device__ __noinline__ float gamma_boost(const PhiloxStream s, float k) {
+    uint32_t w[4];
+    philox4x32_10(s.draw, s.stream, 0xFFFFu, 1u, s.k0, s.k1, w);
+    return __powf(u01(w[0]), 1.0f / k);
+}
+
+// Marsaglia-Tsang rejection iterations 1.. (iteration 0 is the precomputed pair); d = kk-1/3, c = 1/sqrt(9d)
+__device__ __noinline__ float gamma_retry(const PhiloxStream s, float d, float c) {
     float out = d;
-    for (uint32_t it = 0; it < 64u; ++it) {
-        philox_nl(s.draw, s.stream, it, 0u, s.k0, s.k1, w);
-        float x = normal01(w);
-        float v = 1.0f + c * x;
+    for (uint32_t it = 1; it < 64u; ++it) {
+        XU r = raw_xu(s.k0, s.k1, s.stream, s.draw, it);
+        float v = 1.0f + c * r.x;
         if (v <= 0.0f) continue;
         v = v * v * v;
-        float u = u01(w[2]);
-        float x2 = x * x;
+        float x2 = r.x * r.x;
         out = d * v;
-        if (u < 1.0f - 0.0331f * x2 * x2) break;
-        if (__logf(u) < 0.5f * x2 + d * (1.0f - v + __logf(v))) break;
+        if (r.u < 1.0f - 0.0331f * x2 * x2) break;
+        if (__logf(r.u) < 0.5f * x2 + d * (1.0f - v + __logf(v))) break;
     }
-    return out * theta * boost;
+    return out;
 }
 
-// value of one sample BEFORE the max(0, .) clamp; kind/d0/d1 are the derived parameters
-__device__ __forceinline__ float sample_raw(const PhiloxStream& s, int kind, float d0, float d1, uint32_t sub) {
-    uint32_t w[4];
+__device__ __forceinline__ float gamma_from_xu(const PhiloxStream& s, float k, float theta, float d, float c, XU r) {
+    float g;
+    float v = 1.0f + c * r.x;
+    float v3 = v * v * v;
+    float x2 = r.x * r.x;
+    bool ok = v > 0.0f;
+    if (ok) ok = (r.u < 1.0f - 0.0331f * x2 * x2) || (__logf(r.u) < 0.5f * x2 + d * (1.0f - v3 + __logf(v3)));
+    g = ok ? d * v3 : gamma_retry(s, d, c);
+    if (k < 1.0f) g *= gamma_boost(s, k);
+    return g * theta;
+}
+
+// value of one sample BEFORE the max(0, .) clamp; (d0,d1) derived parameters, (md,mc) Marsaglia-Tsang constants
+__device__ __forceinline__ float sample_from_xu(const PhiloxStream& s, int kind, float d0, float d1, float md, float mc,
+                                                XU r) {
     switch (kind) {
-    case 1: // uniform(a,b)
-        philox_nl(s.draw, s.stream, sub, 2u, s.k0, s.k1, w);
-        return d0 + (d1 - d0) * u01(w[0]);
-    case 2: case 3:
-        return gamma_mt(s, d0, d1);
-    case 4: // expo(mean)
-        philox_nl(s.draw, s.stream, sub, 2u, s.k0, s.k1, w);
-        return -d0 * __logf(u01(w[0]));
-    case 5: // normal(mu, sigma)
-        philox_nl(s.draw, s.stream, sub, 2u, s.k0, s.k1, w);
-        return d0 + d1 * normal01(w);
-    default:
-        return d0;
+    case 1: return d0 + (d1 - d0) * r.u;                     // uniform(a,b)
+    case 2: case 3: return gamma_from_xu(s, d0, d1, md, mc, r);
+    case 4: return -d0 * __logf(r.u);                        // expo(mean)
+    case 5: return d0 + d1 * r.x;                            // normal(mu, sigma)
+    default: return d0;
     }
 }
 
-// DistributionGenerator.random_number (utils.py:42-67): max(0, np.float32(v))
-__device__ __noinline__ float draw_scalar_philox(const PhiloxStream s, int kind, float d0, float d1) {
-    float v = sample_raw(s, kind, d0, d1, 0u);
-    return v > 0.0f ? v : 0.0f;
-}
-
-// DistributionGenerator.sum_random_numbers_batch (utils.py:69-102)
-__device__ __noinline__ double draw_batch_philox(const PhiloxStream s, int kind, float d0, float d1, double raw0,
-                                                    int count) {
-    if (count <= 0) return 0.0;
-    switch (kind) {
-    case 0: return (double)count * raw0;
-    case 2: case 3: return (double)gamma_mt(s, d0 * (float)count, d1);
-    case 4: return (count == 1) ? (double)sample_raw(s, 4, d0, d1, 0u) : (double)gamma_mt(s, (float)count, d0);
-    case 1: {
-        float t = 0.0f;
-        for (int i = 0; i < count; ++i) t += sample_raw(s, 1, d0, d1, 16u + (uint32_t)i);
-        return (double)t;
+// sums of count > 1 samples (utils.py:83-98): closed forms for gamma/erlang/expo, loops otherwise
+__device__ __noinline__ float batch_many(const PhiloxStream s, int kind, float d0, float d1, int count, XU r) {
+    if (kind == 2 || kind == 3 || kind == 4) {
+        float k = kind == 4 ? (float)count : d0 * (float)count;
+        float th = kind == 4 ? d0 : d1;
+        float kk = k < 1.0f ? k + 1.0f : k;
+        float d = kk - (1.0f / 3.0f);
+        return gamma_from_xu(s, k, th, d, rsqrtf(9.0f * d), r);
     }
-    default: { // normal: per-sample float32 clamp (utils.py:97-98)
-        float t = 0.0f;
-        for (int i = 0; i < count; ++i) {
-            float v = sample_raw(s, 5, d0, d1, 16u + (uint32_t)i);
-            t += v > 0.0f ? v : 0.0f;
-        }
-        return (double)t;
+    float t = 0.0f;
+    for (int i = 0; i < count; ++i) {
+        XU q = i == 0 ? r : raw_xu(s.k0, s.k1, s.stream, s.draw, 16u + (uint32_t)i);
+        float v = sample_from_xu(s, kind, d0, d1, 0.0f, 0.0f, q);
+        t += (kind == 5 && !(v > 0.0f)) ? 0.0f : v;          // normal: per-sample float32 clamp
     }
-    }
+    return t;
 }
 #endif
 

@@ -86,6 +86,18 @@ def scenario_table():
             r["setup"] = {"dist": "constant", "params": [0, 0]}
     sim_t = dict(sim, run_until=2501, warmup=400, scheduler_interval=24, cb_target_level=120)
     out["dbr_typed"] = dict(cfg=sim_t, resources=res_t, products=prod, policy="dbr", seed=91421, patches=["P2", "P3"])
+    # resource `queue` records (log_queues=True; the shipped configs misspell the key)
+    simq, resq, prodq, _ = _example("simple_scheduler")
+    simq.pop("print_mode", None)
+    simq.update(run_until=300, warmup=40, memory_size=100000, log_queues=True)
+    out["ss_queues"] = dict(cfg=simq, resources=resq, products=prodq, policy="base", seed=806309, patches=[])
+    # SimPy ValueError cases: negative batch delay, Container.put(0)
+    cfg, res, prod = sc.toy2(run_until=400)
+    prod["p1"]["processes"]["s1"]["processing_time"] = {"dist": "uniform", "params": [0.2, 2.0]}   # a < 0
+    out["err_negdelay"] = dict(cfg=cfg, resources=res, products=prod, policy="base", seed=5, patches=[])
+    cfg, res, prod = sc.toy2(run_until=400)
+    prod["p1"]["demand"]["quantity"] = {"dist": "uniform", "params": [0.9, 0.5]}                   # round(x,0) hits 0
+    out["err_amount"] = dict(cfg=cfg, resources=res, products=prod, policy="base", seed=5, patches=[])
     return out
 
 

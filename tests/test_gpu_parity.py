@@ -4,7 +4,7 @@ reference's own variate tapes (replay mode)."""
 import numpy as np
 import pytest
 
-from conftest import GOLDEN_NAMES, load_golden
+from conftest import ERROR_NAMES, GOLDEN_NAMES, load_golden
 
 pytestmark = pytest.mark.gpu
 
@@ -106,3 +106,51 @@ def test_philox_dbr_matches_oracle_replay(repair):
     cfg = dict(sim, run_until=1501, warmup=200)
     cfg.pop("print_mode", None)
     _oracle_vs_gpu_philox(cfg, res, prod, "dbr", n=8, check=(0, 7), dbr_repair=repair)
+
+
+@pytest.mark.parametrize("name,status", list(zip(ERROR_NAMES, (1, 2))))
+def test_value_error_cases_become_status_codes(name, status):
+    """What makes SimPy raise inside env.run() is a per-replication status; records before the abort still match."""
+    import torch
+
+    from manusim_b200.engine import decode_log
+
+    g = load_golden(name)
+    eng, t = _engine(g["scenario"])
+    res = eng.run(3, tapes=[{k: g["tape_" + k] for k in "ABCD"}] * 3, n_log_reps=3, log_cap=4096)
+    torch.cuda.synchronize()
+    assert (res.status.cpu().numpy() == status).all()
+    ring, tm, val, _ = decode_log(res.log[1].cpu().numpy(), int(res.log_count[1]))
+    assert np.array_equal(ring, g["ring"].astype(np.uint32))
+    assert np.array_equal(tm, g["time"]) and np.array_equal(val, g["value"])
+
+
+def test_factory_simulation_raises_like_simpy():
+    from manusim_b200.factory_sim import FactorySimulation
+
+    g = load_golden("err_amount")
+    s = g["scenario"]
+    sim = FactorySimulation(s["cfg"], s["resources"], s["products"], print_mode="none")
+    sim.reset_simulation(s["seed"], None, tapes={k: g["tape_" + k] for k in "ABCD"})
+    with pytest.raises(ValueError, match="amount"):
+        sim.run_simulation()
+
+
+def test_config2_ten_thousand_deterministic_replications_equal_the_oracle_trace():
+    """BASELINE config #2: every one of 10 000 replications of the all-constant job shop must equal the single
+    reference trace (seeds are irrelevant when nothing is random)."""
+    import torch
+
+    from manusim_b200.engine import decode_log
+
+    g = load_golden("ss_det")
+    eng, t = _engine(g["scenario"])
+    n = 10000
+    res = eng.run(n, seed=123456, n_log_reps=4, log_cap=len(g["ring"]) + 8)
+    torch.cuda.synchronize()
+    assert (res.status == 0).all() and (res.n_events == g["steps"]).all()
+    assert (res.acc_sum == res.acc_sum[0]).all() and (res.acc_cnt == res.acc_cnt[0]).all()
+    for i in range(4):
+        ring, tm, val, _ = decode_log(res.log[i].cpu().numpy(), int(res.log_count[i]))
+        assert np.array_equal(ring, g["ring"].astype(np.uint32))
+        assert np.array_equal(tm, g["time"]) and np.array_equal(val, g["value"])

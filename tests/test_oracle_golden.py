@@ -3,7 +3,7 @@ against golden vectors produced by executing the UNMODIFIED reference (oracle/ge
 import numpy as np
 import pytest
 
-from conftest import GOLDEN_NAMES, ORACLE_POLICY, load_golden
+from conftest import ERROR_NAMES, GOLDEN_NAMES, ORACLE_POLICY, load_golden
 from oracle.factory_oracle import metrics_from_trace, run_oracle
 
 FAST = [n for n in GOLDEN_NAMES if n not in ("js20_ondue", "js20_breakdowns")]
@@ -66,3 +66,13 @@ def test_appendix_c_microtrace():
     assert sel(util_rA)[:2] == [(14.0, 4.0), (24.0, 4.0)]
     assert sel(setup_rB)[0] == (14.0, 0.5)
     assert sel(flow)[0] == (20.5, 10.5)
+
+
+@pytest.mark.parametrize("name", ERROR_NAMES)
+def test_oracle_reproduces_reference_value_errors(name):
+    """SimPy ValueError cases (negative delay, Container amount <= 0): same records before the abort, same message."""
+    g = load_golden(name)
+    o = _run(g)
+    assert g["error"].startswith("ValueError") and o["error"] == g["error"]
+    for k in ("ring", "time", "value", "tape_A", "tape_B", "tape_C"):
+        assert np.array_equal(o[k].view(np.uint8), g[k].view(np.uint8)), k

@@ -45,7 +45,7 @@ def workload_spec(name, run_until=None):
         a = scenarios.jobshop20(run_until=ru, warmup=wu, mode="asReady")
         b = scenarios.jobshop20(run_until=ru, warmup=wu, mode="onDue")
         return {"name": name, "parts": [(a, "fifo", 0, 2), (b, "fifo", 1, 2)], "run_until": ru, "warmup": wu,
-                "pools": [(0, 0), (0, 160)],     # (production-order, demand-order) pool sizes; onDue keeps orders until due
+                "pools": [(0, 128), (0, 224)],     # (production-order, demand-order) pool sizes; onDue keeps orders until due
                 "desc": f"jobshop20 (BASELINE config #4: R=20,P=10, setups, TBF/TTR breakdowns, even=asReady/odd=onDue, "
                         f"run_until={ru}, warmup={wu})"}
     if name == "simple_det":
@@ -58,18 +58,10 @@ def workload_spec(name, run_until=None):
     raise SystemExit(f"unknown workload {name}")
 
 
-def splitmix64(x):
-    x = (x + np.uint64(0x9E3779B97F4A7C15))
-    x = (x ^ (x >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)
-    x = (x ^ (x >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)
-    return x ^ (x >> np.uint64(31))
-
-
 def rep_keys(seed, idx):
-    """Same mapping as msim::rep_key (csrc/philox.cuh): key = f(experiment seed, GLOBAL replication index)."""
-    with np.errstate(over="ignore"):
-        idx = idx.astype(np.uint64)
-        return splitmix64(np.uint64(seed) ^ splitmix64(idx + np.uint64(0x632BE59BD9B4E019)))
+    from manusim_b200.engine import rep_keys as _rk
+
+    return _rk(seed, idx)
 
 
 # --------------------------------------------------------------------------------------------- clocks
@@ -201,6 +193,7 @@ def main():
     ap.add_argument("--max-do", type=int, default=0, help="demand-order pool per replication (0 = library default)")
     ap.add_argument("--fifo", type=int, default=0, help="zero-delay event ring capacity (0 = library default)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-retry", action="store_true", help="do not re-run pool-overflow replications with big pools")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3
@@ -253,6 +246,7 @@ def main():
             p["seeds_host"].copy_(torch.from_numpy(keys.view(np.int64)))
 
     sim_events = []
+    retried = [0]
 
     def device_step(step, timed):
         set_seeds(step)
@@ -266,6 +260,8 @@ def main():
             e1.record(stream)
             if timed:
                 sim_events.append((e0, e1, p))
+            if not args.no_retry:      # congested replications that overflowed the shared-memory pools: re-run on the big-pool twin
+                retried[0] += p["eng"].retry_overflow(p["res"], rep_seeds=p["seeds_dev"])
             p["eng"].reduce(p["res"], out=stats, stream=stream)
         if world > 1:
             dist.all_reduce(stats)
@@ -370,6 +366,7 @@ def main():
             "e2e": {"value": e2e_value, "unit": "events/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
             "gpu_launches": (2 * len(parts)) * args.steps,
             "failed_replications": int(fail_total.item()),
+            "pool_overflow_replications_rerun": retried[0],
             "status_histogram": fail_codes.tolist(),
             "engine": {k: parts[0]["eng"].info[k] for k in ("smem_per_replication", "warps_per_block", "blocks_per_sm",
                                                              "regs_per_thread", "n_sms")},

@@ -31,6 +31,10 @@ struct Scal {
     uint32_t draw[4];       // per-stream draw index (A,B,C,D)
     uint32_t tlen[4];       // replay: tape lengths
     const void* tbase[4];   // replay: tape base pointers of this replication
+    // lane-0 loop state that is touched rarely (see Sim in msim_kernel.cu)
+    double x_now_d;
+    uint32_t x_uqh, x_uqt, x_logc, x_tseq, x_same_left, x_pending, x_rb_need, x_now_py, x_sel_req;
+    int32_t x_status;
     uint32_t k0, k1;        // Philox replication key
     uint32_t rb_base[3];    // draw index held by slot 0 of the precomputed (x,u) buffer of streams A,B,C
     uint32_t n_timeouts;

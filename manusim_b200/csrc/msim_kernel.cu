@@ -110,25 +110,25 @@ struct Sim {
     const unsigned char* tb;  // block-shared tables
     Scal* sc;
     long long rep;
-    // ---- lane-0 state kept in registers
+    // ---- lane-0 state kept in registers (touched by every micro-event)
     float now;
     uint32_t warm;
-    uint32_t nqh, nqt, uqh, uqt;
-    uint32_t nstage, logc;
-    uint32_t nev, tseq, same_left;
-    int status;
-    uint32_t pending;
+    uint32_t nqh, nqt;
+    uint32_t nstage;
+    uint32_t nev;
     uint32_t attn;
-    uint32_t rb_need;         // bit s: the precomputed (x,u) buffer of stream s is (nearly) used up
-    // DBR only: exact python-typed clock (now is its float32 view) and the pending cooperative dispatch request
-    double now_d;
-    uint32_t now_py;
-    uint32_t sel_req;
+    // ---- lane-0 state that lives in the shared-memory slab (touched rarely; keeps the register budget at the
+    //      48-warps-per-SM level): references into Scal
+    uint32_t &uqh, &uqt, &logc, &tseq, &same_left, &pending, &rb_need, &now_py, &sel_req;
+    int& status;
+    double& now_d;            // DBR only: exact python-typed clock (now is its float32 view)
     static constexpr bool DBR = POLICY == MSIM_POLICY_DBR;
     static constexpr bool PRIO = POLICY == MSIM_POLICY_MAX_PRIORITY || POLICY == MSIM_POLICY_EDD;
 
-    __device__ __forceinline__ Sim(const KParams& p_, unsigned char* sb_, const unsigned char* tb_)
-        : p(p_), sb(sb_), tb(tb_) { sc = reinterpret_cast<Scal*>(sb + p.lay.scal); }
+    __device__ __forceinline__ Sim(const KParams& p_, unsigned char* sb_, const unsigned char* tb_, Scal* sc_)
+        : p(p_), sb(sb_), tb(tb_), sc(sc_), uqh(sc_->x_uqh), uqt(sc_->x_uqt), logc(sc_->x_logc), tseq(sc_->x_tseq),
+          same_left(sc_->x_same_left), pending(sc_->x_pending), rb_need(sc_->x_rb_need), now_py(sc_->x_now_py),
+          sel_req(sc_->x_sel_req), status(sc_->x_status), now_d(sc_->x_now_d) {}
 
 #define ARR(T, field) (reinterpret_cast<T*>(sb + p.lay.field))
 #define TAB(T, field) (reinterpret_cast<const T*>(p.tblob + p.lay.field))
@@ -951,14 +951,14 @@ __device__ __forceinline__ void warp_flush(const KParams& p, const unsigned char
 
 // ---------------------------------------------------------------------------------------------------------
 template <int POLICY, int RNG>
-__global__ void __launch_bounds__(256, 5) sim_kernel(const __grid_constant__ KParams p) {
+__global__ void __launch_bounds__(256, 6) sim_kernel(const __grid_constant__ KParams p) {
     extern __shared__ __align__(16) unsigned char smem[];
     const Lay& L = p.lay;
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
     unsigned char* sb = smem + (size_t)warp * L.slab_bytes;
-    Sim<POLICY, RNG> s(p, sb, smem);
-    Scal* sc = s.sc;
+    Scal* sc = reinterpret_cast<Scal*>(sb + L.scal);
+    Sim<POLICY, RNG> s(p, sb, smem, sc);
     const bool on_due = p.delivery_mode == MSIM_DELIVERY_ON_DUE;
     constexpr bool DBR = POLICY == MSIM_POLICY_DBR;
     const uint32_t until_bits = __float_as_uint(p.run_until);

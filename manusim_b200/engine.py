@@ -21,6 +21,21 @@ STATUS_TEXT = {0: "ok", 1: "Negative delay (SimPy ValueError)", 2: "Container am
                6: "replay tape exhausted", 7: "WIP get blocked (unsupported)", 8: "not run"}
 
 
+def _splitmix64(x):
+    x = (x + np.uint64(0x9E3779B97F4A7C15))
+    x = (x ^ (x >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)
+    x = (x ^ (x >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)
+    return x ^ (x >> np.uint64(31))
+
+
+def rep_keys(seed: int, global_index) -> np.ndarray:
+    """Philox replication keys, same mapping as msim::rep_key (csrc/philox.cuh): a function of the experiment
+    seed and the GLOBAL replication index, hence independent of how replications are sharded."""
+    with np.errstate(over="ignore"):
+        idx = np.asarray(global_index).astype(np.uint64)
+        return _splitmix64(np.uint64(seed & 0xFFFFFFFFFFFFFFFF) ^ _splitmix64(idx + np.uint64(0x632BE59BD9B4E019)))
+
+
 def _dist_array(dists):
     arr = (_lib.Dist * len(dists))()
     for i, d in enumerate(dists):
@@ -164,6 +179,42 @@ class BatchEngine:
             _lib.check(self.lib.msim_run(self.handle, C.byref(a)))
         out._keep = keep
         return out
+
+    def retry_overflow(self, res: BatchResult, seed: int = 0, rep_offset: int = 0, rep_seeds=None) -> int:
+        """Replications that ran out of shared-memory pool slots (status 3/4/5: the factory got more congested than
+        the configured pools) are re-simulated with the largest pools on a twin engine and patched into `res`.
+        Philox mode only (keys are per replication, so the re-run reproduces the same trajectory).  Synchronises.
+        Returns the number of replications re-run."""
+        torch = self.torch
+        torch.cuda.synchronize(self.device)
+        st = res.status
+        bad = torch.nonzero((st >= 3) & (st <= 5)).flatten()
+        if bad.numel() == 0:
+            return 0
+        if getattr(self, "_big", None) is None:
+            import copy
+
+            t = copy.copy(self.tables)
+            t.max_production_orders, t.max_demand_orders, t.fifo_capacity = 250, 250, 256
+            self._big = BatchEngine(t, self.device.index)
+        idx = bad.cpu().numpy()
+        if rep_seeds is not None:
+            rs = rep_seeds.cpu().numpy() if torch.is_tensor(rep_seeds) else np.asarray(rep_seeds)
+            keys = rs.view(np.uint64)[idx] if rs.dtype != np.uint64 else rs[idx]
+        else:
+            keys = rep_keys(seed, idx.astype(np.int64) + rep_offset)
+        n_log = int((idx < (res.log.shape[0] if res.log is not None else 0)).sum())
+        sub = self._big.run(len(idx), rep_seeds=np.ascontiguousarray(keys),
+                            n_log_reps=len(idx) if n_log else 0, log_cap=res.log.shape[1] if n_log else 0)
+        torch.cuda.synchronize(self.device)
+        for f in ("acc_sum", "acc_cnt", "n_events", "n_timeouts", "status"):
+            getattr(res, f)[bad] = getattr(sub, f)
+        if n_log:
+            for j, i in enumerate(idx):
+                if i < res.log.shape[0]:
+                    res.log[i] = sub.log[j]
+                    res.log_count[i] = sub.log_count[j]
+        return int(bad.numel())
 
     def alloc(self, n_reps: int, n_log_reps: int = 0, log_cap: int = 0) -> BatchResult:
         torch = self.torch

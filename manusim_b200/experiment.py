@@ -99,6 +99,7 @@ class ExperimentRunner:
         start = time.time()
         keys = np.array(seeds[lo:hi], dtype=np.uint64)
         res = eng.run(n, rep_seeds=keys, rep_offset=lo, n_log_reps=n_log, log_cap=self.log_capacity if n_log else 0)
+        eng.retry_overflow(res, rep_seeds=keys)
         mom = eng.reduce(res)
         if world > 1:
             dist.all_reduce(mom)

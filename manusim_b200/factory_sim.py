@@ -176,6 +176,8 @@ class FactorySimulation:
         seed = 0 if self.seed is None else int(self.seed)
         res = eng.run(1, seed=seed, tapes=[self._tapes] if self._tapes is not None else None,
                       n_log_reps=n_log, log_cap=cap if n_log else 0)
+        if self._tapes is None:
+            eng.retry_overflow(res, seed=seed)
         torch.cuda.synchronize(eng.device)
         status = int(res.status[0])
         if status in (1, 2):

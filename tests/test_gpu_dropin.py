@@ -180,3 +180,24 @@ def test_philox_statistics_agree_with_reference_generators():
         assert abs(a.mean() - b.mean()) <= 4.5 * se + 1e-9, (variable, key, a.mean(), b.mean(), se)
         checked += 1
     assert checked > 100
+
+
+def test_pool_overflow_is_retried_with_big_pools():
+    """Tiny pools overflow (status 3/4); retry_overflow re-runs exactly those replications on the big-pool twin and the
+    patched results equal a run that had big pools from the start."""
+    import torch
+
+    from manusim_b200 import BatchEngine, compile_scenario, scenarios
+
+    cfg, res, prod = scenarios.jobshop20(run_until=600, warmup=50)
+    small = BatchEngine(compile_scenario(cfg, res, prod, max_production_orders=24, max_demand_orders=24))
+    big = BatchEngine(compile_scenario(cfg, res, prod, max_production_orders=250, max_demand_orders=250, fifo_capacity=256))
+    a = small.run(64, seed=3)
+    torch.cuda.synchronize()
+    n_bad = int(((a.status >= 3) & (a.status <= 5)).sum())
+    assert n_bad > 0
+    assert small.retry_overflow(a, seed=3) == n_bad
+    b = big.run(64, seed=3)
+    torch.cuda.synchronize()
+    assert (a.status == 0).all()
+    assert torch.equal(a.acc_sum, b.acc_sum) and torch.equal(a.n_events, b.n_events)

@@ -55,6 +55,18 @@ def workload_spec(name, run_until=None):
         cfg = dict(sim, run_until=ru, warmup=50)
         return {"name": name, "parts": [((cfg, res, prod), "max_priority", 0, 1)], "run_until": ru, "warmup": 50,
                 "desc": f"simple_scheduler deterministic (BASELINE config #2, run_until={ru})"}
+    if name in ("toc_dbr", "toc_dbr_shipped"):
+        sim, res, prod, _ = scenarios.load_example("toc_dbr")
+        ru = run_until or 200001
+        wu = ru // 2
+        cfg = dict(sim, run_until=ru, warmup=wu)
+        cfg.pop("print_mode", None)
+        repaired = name == "toc_dbr"
+        return {"name": name, "parts": [((cfg, res, prod), "dbr", 0, 1)], "run_until": ru, "warmup": wu,
+                "dbr_repair": repaired,
+                "desc": f"examples/toc_dbr drum-buffer-rope (BASELINE config #3, "
+                        f"{'repaired: oracle patches P2+P3' if repaired else 'as shipped: oracle patch P2'}, "
+                        f"run_until={ru}, warmup={wu})"}
     raise SystemExit(f"unknown workload {name}")
 
 
@@ -122,7 +134,7 @@ def _oracle_one(task):
     (cfg, res, prod), policy, _, _ = spec["parts"][part_idx]
     cfg = dict(cfg, enable_event_logging=True)
     t0 = time.perf_counter()
-    out = FactoryOracle(cfg, res, prod, seed, policy).run()
+    out = FactoryOracle(cfg, res, prod, seed, policy, dbr_repair=spec.get("dbr_repair", False)).run()
     return out["steps"], time.perf_counter() - t0, len(out["ring"])
 
 
@@ -219,7 +231,8 @@ def main():
     parts = []
     for i, ((cfg, res, prod), policy, phase, period) in enumerate(spec["parts"]):
         mpo, mdo = spec.get("pools", [(0, 0)] * len(spec["parts"]))[i]
-        eng = BatchEngine(compile_scenario(cfg, res, prod, policy=policy, max_production_orders=args.max_po or mpo,
+        eng = BatchEngine(compile_scenario(cfg, res, prod, policy=policy, dbr_repair=spec.get("dbr_repair", False),
+                                           max_production_orders=args.max_po or mpo,
                                            max_demand_orders=args.max_do or mdo, fifo_capacity=args.fifo))
         n = args.reps // period
         parts.append({"eng": eng, "n": n, "phase": phase, "period": period})

@@ -1,0 +1,130 @@
+"""Scenario-sweep front end (BASELINE config #5): a grid of config overrides, every grid point a
+scenario with its own compiled tables, `reps` replications each, all on the GPU(s).
+
+The reference only sweeps through Hydra multirun (examples/*/conf/config.yaml:25-30; experiment.py:16-26 forces
+n_jobs=1 there), i.e. one OS process per grid point running replications one after another.  Here the flattened
+index space (scenario, replication) is split contiguously over the ranks; each rank launches one batch per scenario
+slice it owns and the per-scenario {sum x, sum x^2, n} moments are allreduced once at the end.
+
+Overrides address the reference's config tree with dotted paths, e.g.
+    {"products.*.demand.freq.params.0": [10 / 0.7, 10 / 0.85, 10.0], "products.*.shipping_buffer": [50, 100, 150]}
+(`*` fans out over every key at that level).
+"""
+from __future__ import annotations
+
+import copy
+import itertools
+from typing import Any, Dict, List, Mapping, Sequence, Tuple
+
+import numpy as np
+import pandas as pd
+
+from .experiment import shard_bounds, stats_from_moments
+
+
+def _set_path(tree, path: Sequence[str], value):
+    key = path[0]
+    if key == "*":
+        keys = list(tree.keys()) if isinstance(tree, Mapping) else range(len(tree))
+        for k in keys:
+            if len(path) == 1:
+                tree[k] = value
+            else:
+                _set_path(tree[k], path[1:], value)
+        return
+    if isinstance(tree, list):
+        key = int(key)
+    if len(path) == 1:
+        tree[key] = value
+    else:
+        _set_path(tree[key], path[1:], value)
+
+
+def expand_grid(base: Dict[str, Any], overrides: Dict[str, Sequence[Any]]) -> List[Tuple[Dict[str, Any], Dict[str, Any]]]:
+    """base = {"simulation":..., "resources":..., "products":...}; returns [(point, config tree)] in itertools.product
+    order of the override lists (first key slowest)."""
+    names = list(overrides.keys())
+    out = []
+    for combo in itertools.product(*[overrides[n] for n in names]):
+        tree = copy.deepcopy(base)
+        for name, value in zip(names, combo):
+            _set_path(tree, name.split("."), value)
+        out.append((dict(zip(names, combo)), tree))
+    return out
+
+
+def flat_slices(n_scenarios: int, reps: int, world: int, rank: int) -> List[Tuple[int, int, int]]:
+    """[(scenario, first replication, count)] owned by `rank` when the flattened (scenario, replication) space is
+    split contiguously over `world` ranks."""
+    lo, hi = shard_bounds(n_scenarios * reps, world, rank)
+    out = []
+    s = lo // reps if reps else 0
+    while lo < hi:
+        first = lo - s * reps
+        cnt = min(reps - first, hi - lo)
+        out.append((s, first, cnt))
+        lo += cnt
+        s += 1
+    return out
+
+
+class SweepRunner:
+    def __init__(self, sim_cls, base: Dict[str, Any], overrides: Dict[str, Sequence[Any]], reps: int, seed: int = 0,
+                 sim_kwargs: Dict[str, Any] | None = None):
+        self.sim_cls = sim_cls
+        self.points = expand_grid(base, overrides)
+        self.reps = reps
+        self.seed = seed
+        self.sim_kwargs = sim_kwargs or {}
+        self.moments = None
+        self.events = 0
+
+    def run(self) -> pd.DataFrame:
+        import torch
+        import torch.distributed as dist
+
+        world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
+        rank = dist.get_rank() if world > 1 else 0
+        sims = {}
+        mom = None
+        ev_total = None
+        names = None
+        for s, first, cnt in flat_slices(len(self.points), self.reps, world, rank):
+            if s not in sims:
+                _, tree = self.points[s]
+                sims[s] = self.sim_cls(tree["simulation"], tree["resources"], tree["products"], print_mode="none",
+                                       **self.sim_kwargs)
+            sim = sims[s]
+            eng = sim.engine
+            if mom is None:
+                mom = torch.zeros((len(self.points), eng.K, 3), dtype=torch.float64, device=eng.device)
+                ev_total = torch.zeros((), dtype=torch.int64, device=eng.device)
+                names = sim.tables.ring_names()
+            # replication key = f(seed of the scenario, replication index within the scenario): shard-invariant
+            res = eng.run(cnt, seed=self.seed + 1000003 * s, rep_offset=first)
+            eng.retry_overflow(res, seed=self.seed + 1000003 * s, rep_offset=first)
+            eng.reduce(res, out=mom[s])
+            ev_total += res.n_events.sum()
+        if mom is None:   # a rank without work still has to join the collective
+            sim = self.sim_cls(*[self.points[0][1][k] for k in ("simulation", "resources", "products")],
+                               print_mode="none", **self.sim_kwargs)
+            eng = sim.engine
+            mom = torch.zeros((len(self.points), eng.K, 3), dtype=torch.float64, device=eng.device)
+            ev_total = torch.zeros((), dtype=torch.int64, device=eng.device)
+            names = sim.tables.ring_names()
+        if world > 1:
+            dist.all_reduce(mom)
+            dist.all_reduce(ev_total)
+        torch.cuda.synchronize()
+        self.moments = mom.cpu().numpy()
+        self.events = int(ev_total.item())
+        frames = []
+        for s, (point, _) in enumerate(self.points):
+            st = stats_from_moments(self.moments[s])
+            st.insert(0, "key", [k for _, k in names])
+            st.insert(0, "variable", [v for v, _ in names])
+            for k, v in point.items():
+                st[k] = v
+            st.insert(0, "scenario", s)
+            frames.append(st)
+        return pd.concat(frames, ignore_index=True)

@@ -111,3 +111,24 @@ def test_unknown_hook_override_is_refused():
     assert d.contraint_resource == "r09" and d.scheduler_interval == 48
     with pytest.raises(ValueError, match="run_until must be specified"):
         FactorySimulation({}, res, prod)
+
+
+def test_sweep_grid_and_flat_slices():
+    from manusim_b200.sweep import expand_grid, flat_slices
+
+    sim, res, prod, _ = scenarios.load_example("toc_dbr")
+    base = {"simulation": sim, "resources": res, "products": prod}
+    pts = expand_grid(base, {"products.*.demand.freq.params.0": [12.5, 10.0],
+                             "products.*.shipping_buffer": [50, 100, 150]})
+    assert len(pts) == 6
+    assert pts[0][0] == {"products.*.demand.freq.params.0": 12.5, "products.*.shipping_buffer": 50}
+    assert all(p["shipping_buffer"] == 150 for p in pts[2][1]["products"].values())
+    assert all(p["demand"]["freq"]["params"][0] == 10.0 for p in pts[5][1]["products"].values())
+    assert base["products"]["produto01"]["shipping_buffer"] == 200          # base tree untouched
+    # the flattened (scenario, replication) space is covered exactly once for any world size
+    for n_s, reps, world in ((6, 100, 1), (6, 100, 4), (256, 31250, 8), (3, 7, 5)):
+        seen = np.zeros((n_s, reps), dtype=int)
+        for rank in range(world):
+            for s, first, cnt in flat_slices(n_s, reps, world, rank):
+                seen[s, first:first + cnt] += 1
+        assert (seen == 1).all()

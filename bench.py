@@ -45,7 +45,7 @@ def workload_spec(name, run_until=None):
         a = scenarios.jobshop20(run_until=ru, warmup=wu, mode="asReady")
         b = scenarios.jobshop20(run_until=ru, warmup=wu, mode="onDue")
         return {"name": name, "parts": [(a, "fifo", 0, 2), (b, "fifo", 1, 2)], "run_until": ru, "warmup": wu,
-                "pools": [(0, 128), (0, 224)],     # (production-order, demand-order) pool sizes; onDue keeps orders until due
+                "pools": [(0, 0), (0, 160)],     # (production-order, demand-order) pool sizes; onDue keeps orders until due
                 "desc": f"jobshop20 (BASELINE config #4: R=20,P=10, setups, TBF/TTR breakdowns, even=asReady/odd=onDue, "
                         f"run_until={ru}, warmup={wu})"}
     if name == "simple_det":
@@ -197,7 +197,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="jobshop20")
-    ap.add_argument("--reps", type=int, default=8192, help="replications per GPU per step")
+    ap.add_argument("--reps", type=int, default=16384, help="replications per GPU per step")
     ap.add_argument("--run-until", type=int, default=None)
     ap.add_argument("--log-cap", type=int, default=4096, help="records per replication HBM ring (0 = no log streaming)")
     ap.add_argument("--cpu-workers", type=int, default=0)
@@ -355,7 +355,8 @@ def main():
         dist.barrier()
     t0 = time.perf_counter()
     e2e_events = 0
-    for k in range(args.steps):
+    e2e_steps = min(args.steps, 3)            # same step, fewer repetitions: keeps the default run within minutes
+    for k in range(e2e_steps):
         e2e_events += e2e_step(args.warmup + k)
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
@@ -376,7 +377,8 @@ def main():
                        "l2": "flushed with a 256 MB write between timed steps"},
             "replications_per_sec": reps_total / (total_ms * 1e-3),
             "events_per_replication": events / reps_total,
-            "e2e": {"value": e2e_value, "unit": "events/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+            "e2e": {"value": e2e_value, "unit": "events/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "steps": e2e_steps, "api": "BatchEngine.run_host -> msim_run_host (pinned host buffers)"},
             "gpu_launches": (2 * len(parts)) * args.steps,
             "failed_replications": int(fail_total.item()),
             "pool_overflow_replications_rerun": retried[0],

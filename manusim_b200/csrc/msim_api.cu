@@ -188,6 +188,10 @@ extern "C" int msim_create(const msim_tables_t* t, msim_handle_t* out) {
         L.t_freq = put(fq.data(), fq.size() * sizeof(DDist), 8);
         L.t_qty = put(qt.data(), qt.size() * sizeof(DDist), 8);
         L.t_due = put(du.data(), du.size() * sizeof(DDist), 8);
+        if (L.t_qty != L.t_freq + P * (int)sizeof(DDist) || L.t_due != L.t_qty + P * (int)sizeof(DDist)) {
+            delete h;
+            return fail(MSIM_E_INVALID, "internal: demand tables must be contiguous");
+        }
         L.t_shipbuf = put(sbuf.data(), sbuf.size() * 8, 8);
         L.t_ccrpt = put(cpt.data(), cpt.size() * 8, 8);
         L.t_route_start = put(rs.data(), rs.size() * 2, 2);

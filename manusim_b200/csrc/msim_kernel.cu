@@ -196,6 +196,10 @@ struct Sim {
             if (idx >= sc->tlen[stream]) { fail(MSIM_ST_TAPE_EXHAUSTED); return 0.0f; }
             return __ldg(reinterpret_cast<const float*>(sc->tbase[stream]) + idx);
         }
+        if (d.kind == MSIM_DIST_CONSTANT && p.a.rec_cap == 0) {   // max(0, np.float32(params[0])): no generator involved
+            sc->draw[stream]++;
+            return d.d0 > 0.0f ? d.d0 : 0.0f;
+        }
         return (float)philox_draw_slow(p, sc, ARR(float2, rb), rep, stream, &d, -1);
     }
     __device__ __forceinline__ double draw_batch(const DDist& d, int count) {

@@ -161,7 +161,7 @@ typedef struct msim_host_args {
 typedef struct msim_info {
     int32_t n_rings;                 /* K = 11 P + 4 R + 3 */
     int32_t smem_per_replication;    /* bytes of shared memory one replication (one warp) owns */
-    int32_t smem_tables;             /* bytes of block-shared scenario tables */
+    int32_t smem_tables;             /* bytes of scenario tables (carried in the kernel parameters / constant bank) */
     int32_t warps_per_block;
     int32_t blocks_per_sm;
     int32_t n_sms;

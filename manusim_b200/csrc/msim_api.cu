@@ -1,7 +1,7 @@
 // msim_api.cu -- host side of the C ABI declared in include/msim.h.
 //
-// msim_create compiles the scenario tables into (a) one block-shared table blob that every CTA stages into
-// shared memory and (b) the byte layout of the per-replication shared-memory slab; it then sizes the launch as a
+// msim_create compiles the scenario tables into (a) one table blob carried in the kernel parameters (constant
+// bank) and (b) the byte layout of the per-replication shared-memory slab; it then sizes the launch as a
 // persistent grid of  n_SMs x resident-CTAs-per-SM  blocks whose warps pull replication indices from a global
 // counter (replications have very different lengths, so static striping would leave a long tail).
 #include <cuda_runtime.h>
@@ -30,7 +30,6 @@ struct msim_handle_s {
     int blocks_per_sm[2];
     int regs[2];
     size_t smem_bytes[2];
-    unsigned char* d_tables;
     unsigned long long* d_counter;
     double span;                // run_until - warmup
     // scratch for msim_run_host
@@ -144,7 +143,7 @@ extern "C" int msim_create(const msim_tables_t* t, msim_handle_t* out) {
     L.do_tt = on_due ? take(L.MD * 4, 4) : 0;  // delivery timers exist only in onDue mode
     L.do_eid = on_due ? take(L.MD * 4, 4) : 0;
     L.r_flags = dbr ? take(R, 1) : 0; L.po_relpy = dbr ? take(L.MP, 1) : 0;
-    L.r_phase = take(R, 1); L.r_cur = take(R, 1); L.r_tcur = take(R, 1);
+    L.r_cur = take(R, 1); L.r_tcur = take(R, 1);
     L.r_inh = take(R, 1); L.r_int = take(R, 1); L.r_outh = take(R, 1); L.r_outt = take(R, 1);
     L.p_obh = take(P, 1); L.p_obt = take(P, 1); L.p_fgqh = take(P, 1); L.p_fgqt = take(P, 1);
     L.po_prod = take(L.MP, 1); L.po_done = take(L.MP, 1); L.po_next = take(L.MP, 1); L.po_loc = take(L.MP, 1);
@@ -254,12 +253,10 @@ extern "C" int msim_create(const msim_tables_t* t, msim_handle_t* out) {
         h->blocks_per_sm[rng] = best_blocks;
         h->smem_bytes[rng] = (size_t)best_w * L.slab_bytes;
     }
-    if (cudaMalloc(&h->d_tables, blob.size()) != cudaSuccess || cudaMalloc(&h->d_counter, 8) != cudaSuccess) {
+    if (cudaMalloc(&h->d_counter, 8) != cudaSuccess) {
         delete h;
         return fail(MSIM_E_NOMEM, "cudaMalloc failed");
     }
-    CU(cudaMemcpy(h->d_tables, blob.data(), blob.size(), cudaMemcpyHostToDevice));
-    kp.tables = h->d_tables;
     kp.work_counter = h->d_counter;
     CU(cudaEventCreate(&h->ev0));
     CU(cudaEventCreate(&h->ev1));
@@ -269,7 +266,6 @@ extern "C" int msim_create(const msim_tables_t* t, msim_handle_t* out) {
 
 extern "C" int msim_destroy(msim_handle_t h) {
     if (!h) return 0;
-    cudaFree(h->d_tables);
     cudaFree(h->d_counter);
     if (h->d_scratch) cudaFree(h->d_scratch);
     cudaEventDestroy(h->ev0);

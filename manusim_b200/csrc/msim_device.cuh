@@ -62,7 +62,7 @@ struct Lay {
     int32_t po_rel, po_qty, po_prio, po_tt, po_eid, po_ccr;
     int32_t do_arr, do_due, do_qty, do_tt, do_eid;
     int32_t r_tpy, r_start_d, r_utf_d, r_flags, po_relpy;   // DBR: python-typed clock excursions (Appendix B.2)
-    int32_t r_phase, r_cur, r_tcur, r_inh, r_int, r_outh, r_outt;
+    int32_t r_cur, r_tcur, r_inh, r_int, r_outh, r_outt;
     int32_t p_obh, p_obt, p_fgqh, p_fgqt;
     int32_t po_prod, po_done, po_next, po_loc, do_prod, do_next;
     int32_t scal, slab_bytes;
@@ -74,7 +74,6 @@ struct Lay {
 struct KParams {
     alignas(16) unsigned char tblob[kTabMax];   // scenario tables (routes, distributions): read with LDC, cost no shared memory
     Lay lay;
-    const unsigned char* tables;   // unused (kept for ABI stability of the struct)
     unsigned long long* work_counter;
     float run_until, warmup;       // float32 views (heap comparisons happen at float32 precision, Appendix B.1)
     int32_t delivery_mode, log_queues;

@@ -18,8 +18,11 @@
 //                       the replication's HBM ring; the same flush folds the records into per-ring
 //                       (sum f64, count) accumulators (warm-up filtering happens at emission, as in the
 //                       reference).
-// Scheduling rules (FIFO / max-priority / DBR) are template parameters, so is the variate source
-// (Philox4x32-10 keyed by replication/stream/draw index, or replay of host-recorded tapes).
+// Scheduling rules (FIFO / max-priority / DBR / EDD) are template parameters, so is the variate source
+// (Philox4x32-10 keyed by replication/stream/draw index, or replay of host-recorded tapes).  Scenario tables
+// (routes, distributions) travel in the kernel parameters and are read with LDC; they use no shared memory.
+// Lane 0's loop state is split: what every micro-event touches stays in registers, the rest lives in the slab
+// (`Scal`), which keeps the kernel at 40 registers per thread.
 //
 // Reference anchors are given next to each handler as file:line of /root/reference/src/manusim/factory_sim.py.
 #include <cuda_runtime.h>
@@ -43,7 +46,6 @@ enum Op : uint32_t {
     OP_TO_TICK, OP_INIT_DORDER, OP_TO_DORDER, OP_SEED_PUT, OP_FIN_PUT, OP_DRAIN_GOT,
 };
 
-enum Phase : uint8_t { PH_SETUP = 0, PH_PROC = 1, PH_TTR = 2 };
 enum Loc : uint8_t { LOC_NONE = 0, LOC_IN = 1, LOC_PROC = 2, LOC_OUT = 3, LOC_TRANS = 4 };
 enum Req : int { REQ_ADVANCE = 0, REQ_FLUSH = 1, REQ_DONE = 2, REQ_SELECT = 3 };
 // lane 0 "attention" bits: the fast path of the event loop (pop NORMAL fifo, dispatch) runs while this word is zero
@@ -107,7 +109,6 @@ template <int POLICY, int RNG>
 struct Sim {
     const KParams& p;
     unsigned char* sb;        // this warp's slab
-    const unsigned char* tb;  // block-shared tables
     Scal* sc;
     long long rep;
     // ---- lane-0 state kept in registers (touched by every micro-event)
@@ -125,8 +126,8 @@ struct Sim {
     static constexpr bool DBR = POLICY == MSIM_POLICY_DBR;
     static constexpr bool PRIO = POLICY == MSIM_POLICY_MAX_PRIORITY || POLICY == MSIM_POLICY_EDD;
 
-    __device__ __forceinline__ Sim(const KParams& p_, unsigned char* sb_, const unsigned char* tb_, Scal* sc_)
-        : p(p_), sb(sb_), tb(tb_), sc(sc_), uqh(sc_->x_uqh), uqt(sc_->x_uqt), logc(sc_->x_logc), tseq(sc_->x_tseq),
+    __device__ __forceinline__ Sim(const KParams& p_, unsigned char* sb_, Scal* sc_)
+        : p(p_), sb(sb_), sc(sc_), uqh(sc_->x_uqh), uqt(sc_->x_uqt), logc(sc_->x_logc), tseq(sc_->x_tseq),
           same_left(sc_->x_same_left), pending(sc_->x_pending), rb_need(sc_->x_rb_need), now_py(sc_->x_now_py),
           sel_req(sc_->x_sel_req), status(sc_->x_status), now_d(sc_->x_now_d) {}
 
@@ -962,7 +963,7 @@ __global__ void __launch_bounds__(256, 6) sim_kernel(const __grid_constant__ KPa
     const int warp = threadIdx.x >> 5;
     unsigned char* sb = smem + (size_t)warp * L.slab_bytes;
     Scal* sc = reinterpret_cast<Scal*>(sb + L.scal);
-    Sim<POLICY, RNG> s(p, sb, smem, sc);
+    Sim<POLICY, RNG> s(p, sb, sc);
     const bool on_due = p.delivery_mode == MSIM_DELIVERY_ON_DUE;
     constexpr bool DBR = POLICY == MSIM_POLICY_DBR;
     const uint32_t until_bits = __float_as_uint(p.run_until);

@@ -251,6 +251,7 @@ def main():
     rec_total = torch.zeros((), dtype=torch.int64, device=dev)
     flush_buf = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)   # > 126 MB L2
     stream = torch.cuda.current_stream(dev)
+    side = [torch.cuda.Stream(dev) for _ in parts]
 
     def set_seeds(step):
         for p in parts:
@@ -259,7 +260,7 @@ def main():
             p["seeds_host"].copy_(torch.from_numpy(keys.view(np.int64)))
 
     sim_events = []
-    retried = [0]
+    retried = [0, 0]
 
     def device_step(step, timed):
         set_seeds(step)
@@ -273,8 +274,15 @@ def main():
             e1.record(stream)
             if timed:
                 sim_events.append((e0, e1, p))
-            if not args.no_retry:      # congested replications that overflowed the shared-memory pools: re-run on the big-pool twin
-                retried[0] += p["eng"].retry_overflow(p["res"], rep_seeds=p["seeds_dev"])
+        if not args.no_retry:
+            # congested replications that overflowed the shared-memory pools are re-run on a big-pool twin engine;
+            # the (few, long) re-runs of all parts overlap on side streams
+            ctxs = [p["eng"].retry_launch(p["res"], rep_seeds=p["seeds_dev"], stream=side[i]) for i, p in enumerate(parts)]
+            for p, c in zip(parts, ctxs):
+                retried[0] += p["eng"].retry_collect(c)
+                if timed and c is not None:
+                    retried[1] += 1
+        for p in parts:
             p["eng"].reduce(p["res"], out=stats, stream=stream)
         if world > 1:
             dist.all_reduce(stats)
@@ -387,7 +395,7 @@ def main():
             "events_per_replication": events / reps_total,
             "e2e": {"value": e2e_value, "unit": "events/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "steps": e2e_steps, "api": "BatchEngine.run_host -> msim_run_host (pinned host buffers)"},
-            "gpu_launches": (2 * len(parts)) * args.steps,
+            "gpu_launches": (2 * len(parts)) * args.steps + retried[1],
             "failed_replications": int(fail_total.item()),
             "pool_overflow_replications_rerun": retried[0],
             "status_histogram": fail_codes.tolist(),

@@ -185,12 +185,17 @@ class BatchEngine:
         the configured pools) are re-simulated with the largest pools on a twin engine and patched into `res`.
         Philox mode only (keys are per replication, so the re-run reproduces the same trajectory).  Synchronises.
         Returns the number of replications re-run."""
+        return self.retry_collect(self.retry_launch(res, seed, rep_offset, rep_seeds))
+
+    def retry_launch(self, res: BatchResult, seed: int = 0, rep_offset: int = 0, rep_seeds=None, stream=None):
+        """First half of retry_overflow: waits for `res`, launches the re-run (on `stream`) and returns a context for
+        retry_collect, or None when nothing overflowed.  Lets callers overlap the re-runs of several engines."""
         torch = self.torch
         torch.cuda.synchronize(self.device)
         st = res.status
         bad = torch.nonzero((st >= 3) & (st <= 5)).flatten()
         if bad.numel() == 0:
-            return 0
+            return None
         if getattr(self, "_big", None) is None:
             import copy
 
@@ -204,8 +209,20 @@ class BatchEngine:
         else:
             keys = rep_keys(seed, idx.astype(np.int64) + rep_offset)
         n_log = int((idx < (res.log.shape[0] if res.log is not None else 0)).sum())
-        sub = self._big.run(len(idx), rep_seeds=np.ascontiguousarray(keys),
-                            n_log_reps=len(idx) if n_log else 0, log_cap=res.log.shape[1] if n_log else 0)
+        import contextlib
+
+        with (torch.cuda.stream(stream) if stream is not None else contextlib.nullcontext()):
+            # the key upload and the output allocation must be ordered on the same stream as the kernel
+            sub = self._big.run(len(idx), rep_seeds=np.ascontiguousarray(keys),
+                                n_log_reps=len(idx) if n_log else 0, log_cap=res.log.shape[1] if n_log else 0,
+                                stream=stream)
+        return (res, bad, idx, sub, n_log)
+
+    def retry_collect(self, ctx) -> int:
+        if ctx is None:
+            return 0
+        torch = self.torch
+        res, bad, idx, sub, n_log = ctx
         torch.cuda.synchronize(self.device)
         for f in ("acc_sum", "acc_cnt", "n_events", "n_timeouts", "status"):
             getattr(res, f)[bad] = getattr(sub, f)

@@ -1,0 +1,70 @@
+"""CPU (build container only): the UNMODIFIED reference post-processing (`manusim.metrics.ExperimentMetrics`,
+/root/reference/src/manusim/metrics.py:207-935) must read the run tree our writers produce -- per-run metrics CSVs with
+the pandas index column, `log_*.csv` files -- and arrive at the same per-run values and experiment statistics.
+The tree is built from oracle replications (no GPU here); the writers are the product's (frames_from_values, Logger)."""
+import numpy as np
+import pandas as pd
+import pytest
+
+from oracle import run_reference as rr
+
+pytestmark = pytest.mark.skipif(not rr.reference_available(), reason="/root/reference not mounted")
+
+
+def test_reference_experiment_metrics_reads_our_tree(tmp_path):
+    import yaml
+
+    from manusim_b200 import compile_scenario, scenarios
+    from manusim_b200.experiment import generate_run_seeds, stats_from_moments
+    from manusim_b200.logs import Logger
+    from manusim_b200.metrics import frames_from_values, metric_values
+    from oracle.factory_oracle import metrics_from_trace, run_oracle
+
+    ref = rr.load_reference()
+    import importlib
+
+    metrics_mod = importlib.import_module("manusim.metrics")
+    sim, res, prod, exp = scenarios.load_example("simple_scheduler")
+    cfg = dict(sim, run_until=250, warmup=50, memory_size=100000)
+    t = compile_scenario(cfg, res, prod, policy="max_priority")
+    seeds = generate_run_seeds(exp["exp_seed"], 4)
+    vals = []
+    for i, seed in enumerate(seeds, start=1):
+        o = run_oracle(cfg, res, prod, seed, "max_priority")
+        s, c, _ = metrics_from_trace(o, t.P, t.R, 250, 50)
+        v = metric_values(s, c, t, 200.0)
+        vals.append(v)
+        rf = tmp_path / f"run_{i:03d}"
+        rf.mkdir()
+        for df, name in zip(frames_from_values(v, t), ("products", "resources", "general")):
+            df.to_csv(rf / f"metrics_{name}.csv")
+        lg = Logger.for_tables(t, rf / "logs", 100000)
+        lg.load_stream(t.ring_names(), o["ring"].astype(np.uint32), o["time"], o["value"])
+        lg.save_all_logs()
+        (rf / "run_info.yaml").write_text(yaml.dump({"run_id": i, "seed": seed, "elapsed_time": 0.1,
+                                                     "simulation_end_time": 250, "run_folder": str(rf)}))
+    vals = np.array(vals)
+    em = metrics_mod.ExperimentMetrics(tmp_path)
+    em.read_runs_metrics()
+    rm = em.runs_metrics
+    assert set(rm.columns) >= {"variable", "key", "run", "value"}
+    # per-run values the reference parsed == what we wrote
+    names = t.ring_names()
+    k = names.index(("utilization", "r09"))
+    got = rm[(rm.variable == "utilization") & (rm.key == "r09")].sort_values("run")["value"].to_numpy(dtype=float)
+    np.testing.assert_allclose(got, vals[:, k], rtol=1e-9)
+    k2 = names.index(("flowTime", "produto03"))
+    got2 = rm[(rm.variable == "flowTime") & (rm.key == "produto03")].sort_values("run")["value"].to_numpy(dtype=float)
+    np.testing.assert_allclose(got2, vals[:, k2], rtol=1e-9, equal_nan=True)
+    # experiment statistics: the reference's save_stats runs on the tree; our moments give the same per-key mean/std
+    stats = em.save_stats(0.95, 0.05)
+    assert (tmp_path / "experiment_stats.csv").exists() and (tmp_path / "runs_metrics.csv").exists()
+    assert not stats.empty
+    ok = ~np.isnan(vals)
+    mom = np.stack([np.where(ok, vals, 0).sum(0), np.where(ok, vals ** 2, 0).sum(0), ok.sum(0).astype(float)], axis=1)
+    st = stats_from_moments(mom)
+    np.testing.assert_allclose(st["mean"][k], got.mean(), rtol=1e-12)
+    np.testing.assert_allclose(st["std"][k], got.std(ddof=1), rtol=1e-9)
+    # the reference can also read the raw logs we saved
+    em.read_logs(["utilization"])
+    assert len(em.logs) > 0 and set(em.logs["variable"]) == {"utilization"}

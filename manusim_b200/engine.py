@@ -275,8 +275,10 @@ class BatchEngine:
         return res
 
     def run_host(self, n_reps: int, seed: int = 0, rep_offset: int = 0, tapes=None, rep_seeds=None,
-                 out: Optional[BatchResult] = None, n_log_reps: int = 0, log_cap: int = 0) -> BatchResult:
-        """Host buffers in, host buffers out (H2D + kernel + D2H inside the call, synchronous)."""
+                 out: Optional[BatchResult] = None, n_log_reps: int = 0, log_cap: int = 0,
+                 retry_overflow: bool = True) -> BatchResult:
+        """Host buffers in, host buffers out (H2D + kernel + D2H inside the call, synchronous).  Replications that
+        overflowed the shared-memory pools are re-run on the big-pool twin engine (Philox mode) unless disabled."""
         torch = self.torch
         if out is None:
             out = self.alloc_host(n_reps, n_log_reps, log_cap)
@@ -307,6 +309,26 @@ class BatchEngine:
         with torch.cuda.device(self.device):
             _lib.check(self.lib.msim_run_host(self.handle, C.byref(a)))
         out.kernel_ms = ms.value
+        if retry_overflow and tapes is None:
+            st = out.status.numpy()
+            bad = np.nonzero((st >= 3) & (st <= 5))[0]
+            if len(bad):
+                if getattr(self, "_big", None) is None:
+                    import copy
+
+                    t = copy.copy(self.tables)
+                    t.max_production_orders, t.max_demand_orders, t.fifo_capacity = 250, 250, 256
+                    self._big = BatchEngine(t, self.device.index)
+                if rep_seeds is not None:
+                    rs = rep_seeds.numpy() if torch.is_tensor(rep_seeds) else np.asarray(rep_seeds)
+                    keys = rs.view(np.uint64)[bad]
+                else:
+                    keys = rep_keys(seed, bad.astype(np.int64) + rep_offset)
+                sub = self._big.run_host(len(bad), rep_seeds=np.ascontiguousarray(keys), retry_overflow=False)
+                idx = torch.from_numpy(bad)
+                for f in ("acc_sum", "acc_cnt", "n_events", "n_timeouts", "status"):
+                    getattr(out, f)[idx] = getattr(sub, f)
+                out.kernel_ms += sub.kernel_ms
         return out
 
 

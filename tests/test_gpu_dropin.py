@@ -231,3 +231,19 @@ def test_sweep_runner_matches_per_scenario_runs():
     # more demand (smaller gap) => more lost sales or later deliveries, never fewer released orders
     rel = df[(df.variable == "released") & (df.key == "produto01")].set_index("scenario")["mean"]
     assert np.isfinite(rel).all()
+
+
+def test_host_path_retries_pool_overflow():
+    import torch
+
+    from manusim_b200 import BatchEngine, compile_scenario, scenarios
+
+    cfg, res, prod = scenarios.jobshop20(run_until=600, warmup=50)
+    small = BatchEngine(compile_scenario(cfg, res, prod, max_production_orders=24, max_demand_orders=24))
+    raw = small.run_host(48, seed=3, retry_overflow=False)
+    assert int(((raw.status >= 3) & (raw.status <= 5)).sum()) > 0
+    fixed = small.run_host(48, seed=3)
+    assert (fixed.status == 0).all()
+    big = BatchEngine(compile_scenario(cfg, res, prod, max_production_orders=250, max_demand_orders=250, fifo_capacity=256))
+    ref = big.run_host(48, seed=3)
+    assert torch.equal(fixed.acc_sum, ref.acc_sum) and torch.equal(fixed.n_events, ref.n_events)

@@ -63,7 +63,7 @@ def workload_spec(name, run_until=None):
         cfg.pop("print_mode", None)
         repaired = name == "toc_dbr"
         return {"name": name, "parts": [((cfg, res, prod), "dbr", 0, 1)], "run_until": ru, "warmup": wu,
-                "dbr_repair": repaired,
+                "dbr_repair": repaired, "pools": [(80, 24)],   # rope batches orders; `instantly` frees demand orders at once
                 "desc": f"examples/toc_dbr drum-buffer-rope (BASELINE config #3, "
                         f"{'repaired: oracle patches P2+P3' if repaired else 'as shipped: oracle patch P2'}, "
                         f"run_until={ru}, warmup={wu})"}

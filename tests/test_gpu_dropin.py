@@ -247,3 +247,38 @@ def test_host_path_retries_pool_overflow():
     big = BatchEngine(compile_scenario(cfg, res, prod, max_production_orders=250, max_demand_orders=250, fifo_capacity=256))
     ref = big.run_host(48, seed=3)
     assert torch.equal(fixed.acc_sum, ref.acc_sum) and torch.equal(fixed.n_events, ref.n_events)
+
+
+def test_philox_statistics_agree_with_reference_generators_dbr():
+    """Same check for the DBR model (repaired variant, P2+P3) with TBF/TTR breakdowns, lots > 1 and normal setups."""
+    import torch
+
+    from manusim_b200 import BatchEngine, compile_scenario, scenarios
+    from manusim_b200.metrics import metric_values
+    from oracle.factory_oracle import metrics_from_trace, run_oracle
+    from oracle.variates import run_seeds
+
+    sim, res, prod, _ = scenarios.load_example("toc_dbr")
+    cfg = dict(sim, run_until=4001, warmup=800)
+    cfg.pop("print_mode", None)
+    t = compile_scenario(cfg, res, prod, policy="dbr", dbr_repair=True)
+    n_cpu, n_gpu = 24, 2048
+    cpu = np.array([metrics_from_trace(run_oracle(cfg, res, prod, s, "dbr", dbr_repair=True), t.P, t.R, 4001, 800)[2]
+                    for s in run_seeds(4242, n_cpu)])
+    r = BatchEngine(t).run(n_gpu, seed=99)
+    torch.cuda.synchronize()
+    assert (r.status.cpu().numpy() == 0).all()
+    gpu = metric_values(r.acc_sum.cpu().numpy(), r.acc_cnt.cpu().numpy(), t, 3201.0)
+    checked = 0
+    for k, (variable, key) in enumerate(t.ring_names()):
+        if variable in ("queue", "breakdown", "lostSales", "deliveredLate", "tardiness"):
+            continue
+        a, b = cpu[:, k], gpu[:, k]
+        a, b = a[~np.isnan(a)], b[~np.isnan(b)]
+        if len(a) < n_cpu // 2 or len(b) < n_gpu // 2:
+            continue
+        v = max(a.var(ddof=1), b.var(ddof=1))
+        se = np.sqrt(v / len(a) + v / len(b))
+        assert abs(a.mean() - b.mean()) <= 4.5 * se + 1e-9, (variable, key, a.mean(), b.mean(), se)
+        checked += 1
+    assert checked > 80

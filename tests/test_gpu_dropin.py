@@ -282,3 +282,24 @@ def test_philox_statistics_agree_with_reference_generators_dbr():
         assert abs(a.mean() - b.mean()) <= 4.5 * se + 1e-9, (variable, key, a.mean(), b.mean(), se)
         checked += 1
     assert checked > 80
+
+
+def test_dbr_simulation_dropin_replays_reference_run():
+    """DBRSimulation (examples/toc_dbr) through the drop-in class, replaying the reference's recorded variates."""
+    from manusim_b200.factory_sim import DBRSimulation
+
+    g = load_golden("dbr_repaired")
+    s = g["scenario"]
+    sim = DBRSimulation(s["cfg"], s["resources"], s["products"], print_mode="none", dbr_repair=True)
+    assert sim.contraint_resource == "r09"
+    sim.reset_simulation(s["seed"], None, tapes={k: g["tape_" + k] for k in "ABCD"})
+    sim.run_simulation()
+    assert sim.sim_events == g["steps"]
+    ref = pd.DataFrame(g["metrics"]["resources"])
+    got = sim.resources_metrics()
+    np.testing.assert_allclose(got["utilization"].to_numpy(dtype=float), ref["utilization"].to_numpy(dtype=float), rtol=1e-6)
+    np.testing.assert_allclose(got["setup"].to_numpy(dtype=float), ref["setup"].to_numpy(dtype=float), rtol=1e-6)
+    refp = pd.DataFrame(g["metrics"]["products"])
+    gotp = sim.products_metrics()
+    for col in ("deliveredOntime", "lostSales", "flowTime", "released"):
+        np.testing.assert_allclose(gotp[col].to_numpy(dtype=float), refp[col].to_numpy(dtype=float), rtol=1e-6, equal_nan=True)

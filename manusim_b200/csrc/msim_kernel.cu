@@ -22,7 +22,7 @@
 // (Philox4x32-10 keyed by replication/stream/draw index, or replay of host-recorded tapes).  Scenario tables
 // (routes, distributions) travel in the kernel parameters and are read with LDC; they use no shared memory.
 // Lane 0's loop state is split: what every micro-event touches stays in registers, the rest lives in the slab
-// (`Scal`), which keeps the kernel at 40 registers per thread.
+// (`Scal`), which keeps the kernel at 48 registers per thread with few spills.
 //
 // Reference anchors are given next to each handler as file:line of /root/reference/src/manusim/factory_sim.py.
 #include <cuda_runtime.h>
@@ -956,7 +956,7 @@ __device__ __forceinline__ void warp_flush(const KParams& p, const unsigned char
 
 // ---------------------------------------------------------------------------------------------------------
 template <int POLICY, int RNG>
-__global__ void __launch_bounds__(256, 6) sim_kernel(const __grid_constant__ KParams p) {
+__global__ void __launch_bounds__(256, 5) sim_kernel(const __grid_constant__ KParams p) {
     extern __shared__ __align__(16) unsigned char smem[];
     const Lay& L = p.lay;
     const int lane = threadIdx.x & 31;

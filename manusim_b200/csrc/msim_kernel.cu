@@ -421,11 +421,16 @@ struct Sim {
         mach_select(r);
     }
 
+    // True when the NORMAL event about to be pushed would be the very next one popped (nothing else is pending at
+    // this timestamp: no urgent event, no calendar entry tied on `now`, no flush/dispatch request, empty fifo).
+    // The handler may then run its successor directly (case fall-through) instead of pushing and re-dispatching it.
+    __device__ __forceinline__ bool alone() const { return (attn | (nqh ^ nqt)) == 0u; }
+
     // ------------------------------------------------------------------ one micro-event
     __device__ __forceinline__ void dispatch(uint32_t ev) {
         const uint32_t op = ev & 0xFFu;
-        const int a = (ev >> 8) & 0xFF;
-        const int b = (ev >> 16) & 0xFF;
+        int a = (ev >> 8) & 0xFF;
+        int b = (ev >> 16) & 0xFF;
         nev++;
         switch (op) {
         case OP_TO_WARMUP:                                       // factory_sim.py:97-99
@@ -440,9 +445,10 @@ struct Sim {
             ARR(float, do_due)[d] = __fadd_rn(ARR(float, p_ddue)[a], now);
             ARR(float, do_arr)[d] = now;
             list_append(&sc->inb_head, &sc->inb_tail, ARR(uint8_t, do_next), d);
-            pushN(EV(OP_PUT_INBOUND, a, 0));
-            break;
+            if (!alone()) { pushN(EV(OP_PUT_INBOUND, a, 0)); break; }
+            nev++;                                               // StorePut[inbound] popped right away
         }
+        // fall through
         case OP_PUT_INBOUND:                                     // StorePut[inbound] processed
             if (sc->sched_wait && sc->inb_head != kNone) {
                 uint32_t d = list_pop(&sc->inb_head, &sc->inb_tail, ARR(uint8_t, do_next));
@@ -482,18 +488,21 @@ struct Sim {
             if (DBR) ARR(uint8_t, po_relpy)[b] = (uint8_t)now_py;
             list_append(ARR(uint8_t, r_inh) + first, ARR(uint8_t, r_int) + first, ARR(uint8_t, po_next), b);
             ARR(uint8_t, po_loc)[b] = LOC_IN;
-            pushN(EV(OP_REL_PUT1, first, b));
-            break;
+            if (!alone()) { pushN(EV(OP_REL_PUT1, first, b)); break; }
+            a = first;
+            nev++;                                               // StorePut[input of the first resource] popped right away
         }
+        // fall through
         case OP_REL_PUT1: {                                      // :211-212
             serve_mach(a);
             float q = ARR(float, po_qty)[b];
             if (!(q > 0.0f)) { fail(MSIM_ST_AMOUNT_NONPOSITIVE); break; }
             int prod = ARR(uint8_t, po_prod)[b];
             ARR(float, p_wip)[prod] = __fadd_rn(ARR(float, p_wip)[prod], q);
-            pushN(EV(OP_REL_PUT2, a, b));
-            break;
+            if (!alone()) { pushN(EV(OP_REL_PUT2, a, b)); break; }
+            nev++;                                               // ContainerPut[wip] popped right away
         }
+        // fall through
         case OP_REL_PUT2: {                                      // :214-242
             float q = ARR(float, po_qty)[b];
             int prod = ARR(uint8_t, po_prod)[b];
@@ -518,16 +527,18 @@ struct Sim {
             }
             ARR(uint8_t, r_cur)[a] = (uint8_t)b;
             ARR(uint8_t, po_loc)[b] = LOC_PROC;
-            pushN(EV(OP_MACH_PUTPROC, a, 0));
-            break;
+            if (!alone()) { pushN(EV(OP_MACH_PUTPROC, a, 0)); break; }
+            nev++;                                               // StorePut[processing] popped right away
         }
+        // fall through
         case OP_MACH_PUTPROC: {                                  // :397-421 (setup drawn on every operation, quirk E1)
             float setup = draw_scalar_hot(1, TAB(DDist, t_setup)[a]);
             ARR(float, r_setup)[a] = setup;
             if (warm) emit(ringR(RM_SETUP, a), now, setup);
-            pushN(EV(OP_MACH_REQ, a, 0));
-            break;
+            if (!alone()) { pushN(EV(OP_MACH_REQ, a, 0)); break; }
+            nev++;                                               // Request popped right away
         }
+        // fall through
         case OP_MACH_REQ:                                        // :423
             if (DBR) ARR(uint8_t, r_flags)[a] &= ~F_TIMER_PY;
             timer(a, __fadd_rn(now, ARR(float, r_setup)[a]), EV(OP_TO_SETUP, a, 0));
@@ -585,16 +596,18 @@ struct Sim {
             ARR(float, r_busy)[a] = busy;
             ARR(uint8_t, po_done)[po]++;
             ARR(uint8_t, po_loc)[po] = LOC_NONE;
-            pushN(EV(OP_MACH_GOTPROC, a, 0));
-            break;
+            if (!alone()) { pushN(EV(OP_MACH_GOTPROC, a, 0)); break; }
+            nev++;                                               // StoreGet[processing] popped right away
         }
+        // fall through
         case OP_MACH_GOTPROC: {                                  // :452
             uint32_t po = ARR(uint8_t, r_cur)[a];
             list_append(ARR(uint8_t, r_outh) + a, ARR(uint8_t, r_outt) + a, ARR(uint8_t, po_next), po);
             ARR(uint8_t, po_loc)[po] = LOC_OUT;
-            pushN(EV(OP_MACH_PUTOUT, a, 0));
-            break;
+            if (!alone()) { pushN(EV(OP_MACH_PUTOUT, a, 0)); break; }
+            nev++;                                               // StorePut[output] popped right away
         }
+        // fall through
         case OP_MACH_PUTOUT:                                     // :452-461, then loop top :375-380
             if (((sc->trans_wait >> a) & 1u) && ARR(uint8_t, r_outh)[a] != kNone) {
                 uint32_t po = list_pop(ARR(uint8_t, r_outh) + a, ARR(uint8_t, r_outt) + a, ARR(uint8_t, po_next));
@@ -620,37 +633,60 @@ struct Sim {
         case OP_TRANS_GOT:                                       // _transportation :300-304
             ARR(uint8_t, r_tcur)[a] = (uint8_t)b;
             ARR(uint8_t, po_loc)[b] = LOC_TRANS;
-            pushN(EV(OP_TRANS_PUT, a, 0));
-            break;
+            if (!alone()) { pushN(EV(OP_TRANS_PUT, a, 0)); break; }
+            nev++;                                               // StorePut[transport] popped right away
+            // fall through
         case OP_TRANS_PUT: {                                     // :306-310 / :329-335
             uint32_t po = ARR(uint8_t, r_tcur)[a];
             int prod = ARR(uint8_t, po_prod)[po];
             int total = TAB(uint16_t, t_route_start)[prod + 1] - TAB(uint16_t, t_route_start)[prod];
             ARR(uint8_t, po_loc)[po] = LOC_NONE;
-            pushN(EV(ARR(uint8_t, po_done)[po] == total ? OP_TRANS_GOT2_FINAL : OP_TRANS_GOT2_NEXT, a, 0));
+            const bool last = ARR(uint8_t, po_done)[po] == total;
+            if (last || !alone()) { pushN(EV(last ? OP_TRANS_GOT2_FINAL : OP_TRANS_GOT2_NEXT, a, 0)); break; }
+            nev++;                                               // StoreGet[transport] popped right away
+        }
+        // fall through
+        case OP_TRANS_GOT2_NEXT: {                               // :330-336
+            uint32_t po = ARR(uint8_t, r_tcur)[a];
+            int prod = ARR(uint8_t, po_prod)[po];
+            int nxt = TAB(uint8_t, t_step_res)[TAB(uint16_t, t_route_start)[prod] + ARR(uint8_t, po_done)[po]];
+            list_append(ARR(uint8_t, r_inh) + nxt, ARR(uint8_t, r_int) + nxt, ARR(uint8_t, po_next), po);
+            ARR(uint8_t, po_loc)[po] = LOC_IN;
+            if (!alone()) { pushN(EV(OP_TRANS_PUTIN, a, nxt)); break; }
+            b = nxt;
+            nev++;                                               // StorePut[input of the next resource] popped right away
+        }
+        // fall through
+        case OP_TRANS_PUTIN: {                                   // :336-358
+            serve_mach(b);
+            if (p.log_queues) {
+                float q = ARR(float, po_qty)[ARR(uint8_t, r_tcur)[a]];
+                ARR(float, r_qq)[b] = __fadd_rn(ARR(float, r_qq)[b], q);
+                if (warm) queue_log_add(b, q);
+            }
+            trans_get(a);
             break;
         }
         case OP_TRANS_GOT2_FINAL: {                              // :311
             uint32_t po = ARR(uint8_t, r_tcur)[a];
             int prod = ARR(uint8_t, po_prod)[po];
             ARR(float, p_fg)[prod] = __fadd_rn(ARR(float, p_fg)[prod], ARR(float, po_qty)[po]);
-            pushN(EV(OP_TRANS_FGPUT, a, 0));
-            break;
+            if (!alone()) { pushN(EV(OP_TRANS_FGPUT, a, 0)); break; }
+            nev++;                                               // ContainerPut[finished goods] popped right away
         }
+        // fall through
         case OP_TRANS_FGPUT: {                                   // ContainerPut[FG] processed, then :312
             uint32_t po = ARR(uint8_t, r_tcur)[a];
             int prod = ARR(uint8_t, po_prod)[po];
             serve_fg(prod);
             float q = ARR(float, po_qty)[po];
             float w = ARR(float, p_wip)[prod];
-            if (w >= q) {
-                ARR(float, p_wip)[prod] = __fsub_rn(w, q);
-                pushN(EV(OP_TRANS_WIPGET, a, 0));
-            } else {
-                fail(MSIM_ST_WIP_GET_BLOCKED);
-            }
-            break;
+            if (!(w >= q)) { fail(MSIM_ST_WIP_GET_BLOCKED); break; }
+            ARR(float, p_wip)[prod] = __fsub_rn(w, q);
+            if (!alone()) { pushN(EV(OP_TRANS_WIPGET, a, 0)); break; }
+            nev++;                                               // ContainerGet[wip] popped right away
         }
+        // fall through
         case OP_TRANS_WIPGET: {                                  // :314-326
             uint32_t po = ARR(uint8_t, r_tcur)[a];
             int prod = ARR(uint8_t, po_prod)[po];
@@ -667,25 +703,6 @@ struct Sim {
                 inventory(prod, true, true);
             }
             free_po(po);
-            trans_get(a);
-            break;
-        }
-        case OP_TRANS_GOT2_NEXT: {                               // :330-336
-            uint32_t po = ARR(uint8_t, r_tcur)[a];
-            int prod = ARR(uint8_t, po_prod)[po];
-            int nxt = TAB(uint8_t, t_step_res)[TAB(uint16_t, t_route_start)[prod] + ARR(uint8_t, po_done)[po]];
-            list_append(ARR(uint8_t, r_inh) + nxt, ARR(uint8_t, r_int) + nxt, ARR(uint8_t, po_next), po);
-            ARR(uint8_t, po_loc)[po] = LOC_IN;
-            pushN(EV(OP_TRANS_PUTIN, a, nxt));
-            break;
-        }
-        case OP_TRANS_PUTIN: {                                   // :336-358
-            serve_mach(b);
-            if (p.log_queues) {
-                float q = ARR(float, po_qty)[ARR(uint8_t, r_tcur)[a]];
-                ARR(float, r_qq)[b] = __fadd_rn(ARR(float, r_qq)[b], q);
-                if (warm) queue_log_add(b, q);
-            }
             trans_get(a);
             break;
         }

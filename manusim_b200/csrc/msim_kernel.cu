@@ -118,6 +118,7 @@ struct Sim {
     uint32_t nstage;
     uint32_t nev;
     uint32_t attn;
+    uint32_t force;           // 1 while the machine chain MACH_GOT -> PUTPROC -> REQ runs ahead of the transport chain
     // ---- lane-0 state that lives in the shared-memory slab (touched rarely; keeps the register budget at the
     //      48-warps-per-SM level): references into Scal
     uint32_t &uqh, &uqt, &logc, &tseq, &same_left, &pending, &rb_need, &now_py, &sel_req;
@@ -378,14 +379,15 @@ struct Sim {
         timer(p.lay.R + prod, __fadd_rn(now, gap), EV(OP_TO_DEMAND, prod, 0));
     }
     // order_selection: policy is a compile-time device function
-    __device__ __forceinline__ void mach_select(int r) {
+    // returns kNone unless `chain` is set and an order was picked: then the caller runs MACH_GOT itself
+    __device__ __forceinline__ uint32_t mach_select(int r, bool chain = false) {
         uint32_t h = ARR(uint8_t, r_inh)[r];
-        if (h == kNone) { sc->mach_wait |= 1u << r; return; }   // plain get() on an empty queue
+        if (h == kNone) { sc->mach_wait |= 1u << r; return kNone; }   // plain get() on an empty queue
         uint32_t pick = h;
         if (DBR) {
             // buffer-penetration dispatch (toc_dbr/simulation.py:291-328) needs a scan of every in-flight order:
             // a single queued order is trivially the minimum, otherwise the whole warp computes the priorities
-            if (ARR(uint8_t, po_next)[h] != kNone) { sel_req = (uint32_t)r + 1u; attn |= A_SELECT; return; }
+            if (ARR(uint8_t, po_next)[h] != kNone) { sel_req = (uint32_t)r + 1u; attn |= A_SELECT; return kNone; }
             list_pop(ARR(uint8_t, r_inh) + r, ARR(uint8_t, r_int) + r, ARR(uint8_t, po_next));
         } else if (PRIO) {
             // max(orders, key=priority): first maximum in queue order (simple_scheduler/simulation.py:36)
@@ -407,7 +409,9 @@ struct Sim {
             list_pop(ARR(uint8_t, r_inh) + r, ARR(uint8_t, r_int) + r, ARR(uint8_t, po_next));
         }
         ARR(uint8_t, po_loc)[pick] = LOC_NONE;
+        if (chain) return pick;
         pushN(EV(OP_MACH_GOT, r, pick));
+        return kNone;
     }
     // _production_system loop top   factory_sim.py:375-380
     __device__ __forceinline__ void mach_loop_top(int r) {
@@ -516,7 +520,8 @@ struct Sim {
             nev++;                                               // process-end event
             break;
         }
-        case OP_MACH_GOT: {                                      // _production_system :380-395
+        case OP_MACH_GOT:                                        // _production_system :380-395
+        L_MACH_GOT: {
             if (p.log_queues) {
                 float q = ARR(float, po_qty)[b];
                 ARR(float, r_qq)[a] = __fsub_rn(ARR(float, r_qq)[a], q);
@@ -527,7 +532,7 @@ struct Sim {
             }
             ARR(uint8_t, r_cur)[a] = (uint8_t)b;
             ARR(uint8_t, po_loc)[b] = LOC_PROC;
-            if (!alone()) { pushN(EV(OP_MACH_PUTPROC, a, 0)); break; }
+            if (!(force || alone())) { pushN(EV(OP_MACH_PUTPROC, a, 0)); break; }
             nev++;                                               // StorePut[processing] popped right away
         }
         // fall through
@@ -535,11 +540,12 @@ struct Sim {
             float setup = draw_scalar_hot(1, TAB(DDist, t_setup)[a]);
             ARR(float, r_setup)[a] = setup;
             if (warm) emit(ringR(RM_SETUP, a), now, setup);
-            if (!alone()) { pushN(EV(OP_MACH_REQ, a, 0)); break; }
+            if (!(force || alone())) { pushN(EV(OP_MACH_REQ, a, 0)); break; }
             nev++;                                               // Request popped right away
         }
         // fall through
         case OP_MACH_REQ:                                        // :423
+            force = 0;
             if (DBR) ARR(uint8_t, r_flags)[a] &= ~F_TIMER_PY;
             timer(a, __fadd_rn(now, ARR(float, r_setup)[a]), EV(OP_TO_SETUP, a, 0));
             break;
@@ -608,7 +614,13 @@ struct Sim {
             nev++;                                               // StorePut[output] popped right away
         }
         // fall through
-        case OP_MACH_PUTOUT:                                     // :452-461, then loop top :375-380
+        case OP_MACH_PUTOUT: {                                   // :452-461, then loop top :375-380
+            // Nothing else pending at this timestamp: the transport chain (TRANS_GOT ...) and the machine's next
+            // operation chain (MACH_GOT -> PUTPROC -> REQ) that start here touch disjoint state and emit their records
+            // / draws / calendar entries in the same relative order whether interleaved event by event (SimPy) or run
+            // one after the other, so the machine chain may run right here.  Not for DBR (its dispatch scans observe
+            // order locations) nor with queue logging (both chains write `queue` records).
+            const bool solo = !DBR && !p.log_queues && alone();
             if (((sc->trans_wait >> a) & 1u) && ARR(uint8_t, r_outh)[a] != kNone) {
                 uint32_t po = list_pop(ARR(uint8_t, r_outh) + a, ARR(uint8_t, r_outt) + a, ARR(uint8_t, po_next));
                 ARR(uint8_t, po_loc)[po] = LOC_NONE;
@@ -621,8 +633,17 @@ struct Sim {
             }
             if (warm) emit(ringR(RM_UTIL, a), now, ARR(float, r_busy)[a]);
             nev++;                                               // Release event of the `with` block
+            if (solo && (attn & ~A_FLUSH) == 0u && !(ARR(float, r_utf)[a] >= ARR(float, r_tbf)[a])) {
+                uint32_t pick = mach_select(a, true);
+                if (pick == kNone) break;                        // queue empty: the machine waits
+                b = (int)pick;
+                force = 1;
+                nev++;                                           // FilterStoreGet[input] popped ahead of the transport chain
+                goto L_MACH_GOT;
+            }
             mach_loop_top(a);
             break;
+        }
         case OP_TO_TTR:                                          // _breakdowns :277-289
             if (warm) emit(ringR(RM_BREAKDOWN, a), ARR(float, r_start)[a], round6(__fsub_rn(now, ARR(float, r_start)[a])));
             ARR(float, r_tbf)[a] = draw_scalar(3, TAB(DDist, t_tbf)[a]);
@@ -904,7 +925,7 @@ struct Sim {
     __device__ __forceinline__ void boot() {
         const int R = p.lay.R, P = p.lay.P;
         now = 0.0f; warm = 0; nqh = nqt = uqh = uqt = 0; nstage = 0; logc = 0; nev = 0; tseq = 0; same_left = 0;
-        status = 0; pending = 0; attn = 0; rb_need = (uint32_t)p.rng_streams & 6u;
+        status = 0; pending = 0; attn = 0; force = 0; rb_need = (uint32_t)p.rng_streams & 6u;
         now_d = 0.0; now_py = 1; sel_req = 0;
         for (int r = 0; r < R; ++r) {                            // _start_resources :248-261 (draws at construction)
             const DDist& tb_ = TAB(DDist, t_tbf)[r];

@@ -547,8 +547,12 @@ struct Sim {
         case OP_MACH_REQ:                                        // :423
             force = 0;
             if (DBR) ARR(uint8_t, r_flags)[a] &= ~F_TIMER_PY;
-            timer(a, __fadd_rn(now, ARR(float, r_setup)[a]), EV(OP_TO_SETUP, a, 0));
-            break;
+            {
+                const float t = __fadd_rn(now, ARR(float, r_setup)[a]);
+                if (t != now || !alone()) { timer(a, t, EV(OP_TO_SETUP, a, 0)); break; }
+                nev++;                                           // Timeout(0): lands on this timestamp and is popped right away
+            }
+            // fall through
         case OP_TO_SETUP: {                                      // :425-440
             uint32_t po = ARR(uint8_t, r_cur)[a];
             int prod = ARR(uint8_t, po_prod)[po];
@@ -893,10 +897,15 @@ struct Sim {
 
     // lane 0: run zero-delay events until the warp has to cooperate again.  Order of service at one timestamp
     // (SURVEY Appendix A.8): URGENT fifo -> calendar entries landing on `now` -> NORMAL fifo.
-    __device__ __forceinline__ int drain() {
+    // `first` = the calendar event the warp just selected (0 = none): it runs before anything queued, because the
+    // URGENT fifo is empty whenever the calendar is consulted.
+    __device__ __forceinline__ int drain(uint32_t first) {
         for (;;) {
             uint32_t ev;
-            if (attn) {
+            if (first) {                 // (single dispatch site: the handler switch must not be inlined twice)
+                ev = first;
+                first = 0;
+            } else if (attn) {
                 if (attn & A_STATUS) return REQ_DONE;
                 if (attn & A_SELECT) { attn &= ~A_SELECT; return REQ_SELECT; }
                 if (attn & A_FLUSH) { attn &= ~A_FLUSH; return REQ_FLUSH; }
@@ -1058,13 +1067,14 @@ __global__ void __launch_bounds__(256, 5) sim_kernel(const __grid_constant__ KPa
             }
         }
         __syncwarp();
+        uint32_t first_ev = 0;
         if (lane == 0) s.boot();
         __syncwarp();
 
         // ---- event loop
         for (;;) {
             int req = REQ_ADVANCE;
-            if (lane == 0) req = s.drain();
+            if (lane == 0) { req = s.drain(first_ev); first_ev = 0; }
             req = __shfl_sync(FULLMASK, req, 0);
             uint32_t n = __shfl_sync(FULLMASK, s.nstage, 0);
             if (req == REQ_FLUSH) {
@@ -1121,11 +1131,15 @@ __global__ void __launch_bounds__(256, 5) sim_kernel(const __grid_constant__ KPa
             {
                 const uint32_t* tt = reinterpret_cast<const uint32_t*>(sb + L.tm_time);
                 const uint32_t* te = reinterpret_cast<const uint32_t*>(sb + L.tm_eid);
+                if (L.NT == 32) {          // the common shape (R + P + 2 <= 32): one calendar slot per lane
+                    bt = tt[lane]; be = te[lane]; bslot = lane; leq = 1;
+                } else {
 #pragma unroll 1
-                for (int i = lane; i < L.NT; i += 32) {
-                    const uint32_t t = tt[i], e = te[i];
-                    if (t < bt) { bt = t; be = e; bslot = i; leq = 1; }
-                    else if (t == bt) { leq++; if (e < be) { be = e; bslot = i; } }
+                    for (int i = lane; i < L.NT; i += 32) {
+                        const uint32_t t = tt[i], e = te[i];
+                        if (t < bt) { bt = t; be = e; bslot = i; leq = 1; }
+                        else if (t == bt) { leq++; if (e < be) { be = e; bslot = i; } }
+                    }
                 }
                 if (on_due) {
                     const uint32_t* dt = reinterpret_cast<const uint32_t*>(sb + L.do_tt);
@@ -1210,8 +1224,7 @@ __global__ void __launch_bounds__(256, 5) sim_kernel(const __grid_constant__ KPa
                     ev = EV(OP_TO_DORDER, 0, po);
                     reinterpret_cast<float*>(sb + L.po_tt)[po] = CUDART_INF_F;
                 }
-                s.pending = ev;
-                s.attn |= A_PENDING;
+                first_ev = ev;
             }
             __syncwarp();
         }

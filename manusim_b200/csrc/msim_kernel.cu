@@ -413,15 +413,16 @@ struct Sim {
         pushN(EV(OP_MACH_GOT, r, pick));
         return kNone;
     }
+    // _breakdowns entry: draw the repair time and sleep   factory_sim.py:267-276
+    __device__ __forceinline__ void breakdown_start(int r) {
+        ARR(float, r_start)[r] = now;                                      // breakdown_start, :272
+        float ttr = draw_scalar(3, TAB(DDist, t_ttr)[r]);                  // :275
+        if (DBR) ARR(uint8_t, r_flags)[r] &= ~F_TIMER_PY;
+        timer(r, __fadd_rn(now, ttr), EV(OP_TO_TTR, r, 0));
+    }
     // _production_system loop top   factory_sim.py:375-380
     __device__ __forceinline__ void mach_loop_top(int r) {
-        if (ARR(float, r_utf)[r] >= ARR(float, r_tbf)[r]) {
-            ARR(float, r_start)[r] = now;                                  // breakdown_start, :272
-            float ttr = draw_scalar(3, TAB(DDist, t_ttr)[r]);              // :275
-            if (DBR) ARR(uint8_t, r_flags)[r] &= ~F_TIMER_PY;
-            timer(r, __fadd_rn(now, ttr), EV(OP_TO_TTR, r, 0));
-            return;
-        }
+        if (ARR(float, r_utf)[r] >= ARR(float, r_tbf)[r]) { breakdown_start(r); return; }
         mach_select(r);
     }
 
@@ -637,16 +638,16 @@ struct Sim {
             }
             if (warm) emit(ringR(RM_UTIL, a), now, ARR(float, r_busy)[a]);
             nev++;                                               // Release event of the `with` block
-            if (solo && (attn & ~A_FLUSH) == 0u && !(ARR(float, r_utf)[a] >= ARR(float, r_tbf)[a])) {
-                uint32_t pick = mach_select(a, true);
-                if (pick == kNone) break;                        // queue empty: the machine waits
+            if (ARR(float, r_utf)[a] >= ARR(float, r_tbf)[a]) { breakdown_start(a); break; }   // breakdown first (:376-377)
+            {
+                const bool chain = solo && (attn & ~A_FLUSH) == 0u;
+                uint32_t pick = mach_select(a, chain);
+                if (pick == kNone) break;                        // pushed, queue empty (the machine waits) or DBR scan requested
                 b = (int)pick;
                 force = 1;
                 nev++;                                           // FilterStoreGet[input] popped ahead of the transport chain
                 goto L_MACH_GOT;
             }
-            mach_loop_top(a);
-            break;
         }
         case OP_TO_TTR:                                          // _breakdowns :277-289
             if (warm) emit(ringR(RM_BREAKDOWN, a), ARR(float, r_start)[a], round6(__fsub_rn(now, ARR(float, r_start)[a])));
@@ -736,20 +737,19 @@ struct Sim {
             deliv_get(a);
             break;
         case OP_INIT_SHIP:                                       // :482-549 (onDue with patch P1)
-            if (p.delivery_mode == MSIM_DELIVERY_AS_READY) {
-                fg_get(b, a);
-            } else if (p.delivery_mode == MSIM_DELIVERY_INSTANTLY) {
-                if (ARR(float, p_fg)[a] >= ARR(float, do_qty)[b]) {
-                    fg_get(b, a);
-                } else {
+            // (one finished_goods.get() site for the three delivery modes and the onDue timer: the handler switch is
+            //  instruction-cache bound, inlined copies cost more than the branches)
+            if (p.delivery_mode == MSIM_DELIVERY_INSTANTLY) {
+                if (!(ARR(float, p_fg)[a] >= ARR(float, do_qty)[b])) {      // lost sale: nothing is taken
                     if (warm) {
                         inventory(a, false, true);
                         delivery_records(b, a, false);
                     }
                     nev++;                                       // process-end event
                     free_do(b);
+                    break;
                 }
-            } else {
+            } else if (p.delivery_mode == MSIM_DELIVERY_ON_DUE) {
                 float wait = __fsub_rn(ARR(float, do_due)[b], now);
                 if (wait > 0.0f) {
                     float t = __fadd_rn(now, wait);
@@ -759,11 +759,10 @@ struct Sim {
                         ARR(float, do_tt)[b] = t;
                         ARR(uint32_t, do_eid)[b] = tseq++;
                     }
-                } else {
-                    fg_get(b, a);
+                    break;
                 }
             }
-            break;
+            // fall through
         case OP_TO_SHIP:
             fg_get(b, a);
             break;

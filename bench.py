@@ -341,9 +341,9 @@ def main():
         peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
     achieved = alg_bytes / (kern_ms * 1e-3) / 1e9
     # DRAM traffic per algorithmic byte measured once with `ncu --set full` (profiles/r01_ncu_full_final.csv:
-    # dram read 0.277 GB + write 4.750 GB for 2.341 GB algorithmic): records are streamed as 16-byte slots, twice the
+    # dram read 0.109 GB + write 4.624 GB for 2.341 GB algorithmic): records are streamed as 16-byte slots, twice the
     # 8 bytes the reference's (time,value) float32 pair needs
-    traffic_per_alg_byte = 2.147 if log_cap else None
+    traffic_per_alg_byte = 2.02 if log_cap else None
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": (traffic_per_alg_byte * alg_bytes / max(n_launch, 1)) if traffic_per_alg_byte else None,
                 "traffic_source": "ncu dram__bytes_read.sum+dram__bytes_write.sum of one --set full capture, scaled by "
@@ -351,9 +351,8 @@ def main():
                 "peak_source": peak_src, "kernel": "msim::sim_kernel<policy,rng>",
                 "kernel_ms_per_launch": kern_ms / max(n_launch, 1), "launches": n_launch,
                 "algorithmic_bytes_per_launch": alg_bytes / max(n_launch, 1),
-                "note": "path is instruction-issue / instruction-cache bound, not HBM bound (SURVEY 8(d)): ~127 warp "
-                        "instructions per SimPy event, issue slots 52 % busy, stall_no_instruction dominant "
-                        "(profiles/README.md)",
+                "note": "path is instruction-fetch / issue bound, not HBM bound (SURVEY 8(d)): 86 warp instructions per "
+                        "SimPy event, issue slots 40 % busy, stall_no_instruction dominant (profiles/README.md)",
                 "kernel_share_of_step": kern_ms / sum(step_ms)}
 
     # ---- end to end through the public host-buffer API: pinned H2D of the step's inputs + D2H of its results

@@ -137,6 +137,9 @@ def compile_scenario(config: Mapping, resources: Mapping, products: Mapping, pol
     pf, pq, pd_ = [], [], []
     for p in pnames:
         dm = products[p]["demand"]
+        if dm["freq"].get("dist") == "constant" and not (float(dm["freq"].get("params")[0]) > 0):
+            # `yield env.timeout(0)` for ever: the reference never leaves t = 0 (factory_sim.py:154-175); refuse it here
+            raise ValueError(f"product {p!r}: a constant demand interval of 0 never advances the simulation clock")
         pf.append(compile_dist(dm["freq"]))
         pq.append(compile_dist(dm["quantity"]))
         pd_.append(compile_dist(dm["duedate"]))

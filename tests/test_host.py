@@ -32,6 +32,12 @@ def test_compile_errors_mirror_reference():
         compile_scenario(cfg, bad, prod)
     with pytest.raises(NotImplementedError):
         compile_scenario(cfg, res, prod, policy="edd_custom")
+    import copy
+
+    stuck = copy.deepcopy(prod)
+    stuck["p1"]["demand"]["freq"] = {"dist": "constant", "params": [0]}
+    with pytest.raises(ValueError, match="never advances"):
+        compile_scenario(cfg, res, stuck)
 
 
 def test_dbr_constraint_matches_reference():

@@ -35,10 +35,18 @@ def _worker(rank, world, port, n, K, out):
     dist.destroy_process_group()
 
 
+def _free_port():
+    import socket
+
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
 def test_sharded_moments_allreduce(tmp_path):
     n, K, world = 1001, 37, 2
     out = str(tmp_path / "mom.npy")
-    mp.spawn(_worker, args=(world, 29533, n, K, out), nprocs=world, join=True)
+    mp.spawn(_worker, args=(world, _free_port(), n, K, out), nprocs=world, join=True)
     got = np.load(out)
     rng = np.random.default_rng(11)
     x = rng.gamma(2.0, 1.5, size=(n, K))

@@ -86,6 +86,9 @@ def scenario_table():
             r["setup"] = {"dist": "constant", "params": [0, 0]}
     sim_t = dict(sim, run_until=2501, warmup=400, scheduler_interval=24, cb_target_level=120)
     out["dbr_typed"] = dict(cfg=sim_t, resources=res_t, products=prod, policy="dbr", seed=91421, patches=["P2", "P3"])
+    # DBR release limits (toc_dbr/simulation.py:245-262): CCR load budget per tick and at most 3 CCR releases per tick
+    sim_l = dict(sim, run_until=2001, warmup=300, ccr_release_limit=0.6, order_release_limit=3)
+    out["dbr_limits"] = dict(cfg=sim_l, resources=res, products=prod, policy="dbr", seed=806309, patches=["P2", "P3"])
     # resource `queue` records (log_queues=True; the shipped configs misspell the key)
     simq, resq, prodq, _ = _example("simple_scheduler")
     simq.pop("print_mode", None)

@@ -169,6 +169,9 @@ def _compile_dbr(config, resources, products, t: ScenarioTables, repair: bool) -
     ccr_setup = resources[t.resource_names[ccr]].get("setup", {"params": None}).get("params", [0])[0]
     ccr_pt = np.array([sum([t.step_time[s].raw0 for s in range(t.route_start[p], t.route_start[p + 1])
                             if t.step_resource[s] == ccr]) for p in range(P)], dtype=np.float64)
+    if config.get("sb_update", False) or config.get("cb_update", False):
+        # adjust_shipping_buffer (toc_dbr/simulation.py:357-406) rewrites buffer targets from Python lists at run time
+        raise NotImplementedError("sb_update / cb_update (adaptive DBR buffers) are not supported by the DBR kernel")
     if config.get("min_lotsize", 0):
         # max(replenishment, min_lotsize) turns the lot into a Python int, which changes the dynamic typing of the
         # rope delay (int * float -> float64); not modelled by the DBR kernel yet, so refuse instead of deviating

@@ -96,3 +96,11 @@ def test_golden_scenarios_roundtrip_through_compiler():
         s = load_golden(name)["scenario"]
         t = compile_scenario(s["cfg"], s["resources"], s["products"])
         assert t.n_rings == 11 * t.P + 4 * t.R + 3
+
+
+def test_unsupported_dbr_options_are_refused():
+    sim, res, prod, _ = scenarios.load_example("toc_dbr")
+    for key, val in (("min_lotsize", 2), ("sb_update", True), ("cb_update", True)):
+        with pytest.raises(NotImplementedError):
+            compile_scenario(dict(sim, **{key: val}), res, prod, policy="dbr")
+    compile_scenario(dict(sim, ccr_release_limit=0.6, order_release_limit=3), res, prod, policy="dbr")

@@ -104,3 +104,28 @@ def test_unsupported_dbr_options_are_refused():
         with pytest.raises(NotImplementedError):
             compile_scenario(dict(sim, **{key: val}), res, prod, policy="dbr")
     compile_scenario(dict(sim, ccr_release_limit=0.6, order_release_limit=3), res, prod, policy="dbr")
+
+
+def test_ctypes_mirror_matches_the_c_header(tmp_path):
+    """sizeof / offsetof of every struct in include/msim.h, as gcc lays them out, equal the ctypes mirror in _lib.py."""
+    import subprocess
+
+    from manusim_b200 import _lib
+
+    structs = {"msim_dist_t": _lib.Dist, "msim_tables_t": _lib.Tables, "msim_run_args_t": _lib.RunArgs,
+               "msim_host_args_t": _lib.HostArgs, "msim_info_t": _lib.Info}
+    lines = ['#include <stdio.h>', '#include <stddef.h>', f'#include "{ROOT}/include/msim.h"', 'int main(void) {']
+    for cname, cls in structs.items():
+        lines.append(f'  printf("{cname} %zu\\n", sizeof({cname}));')
+        for fname, *_ in cls._fields_:
+            lines.append(f'  printf("{cname}.{fname} %zu\\n", offsetof({cname}, {fname}));')
+    lines += ['  return 0;', '}']
+    src = tmp_path / "abi.c"
+    src.write_text("\n".join(lines))
+    exe = tmp_path / "abi"
+    subprocess.run(["gcc", "-std=c11", "-o", str(exe), str(src)], check=True)
+    out = dict(l.split() for l in subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.splitlines())
+    for cname, cls in structs.items():
+        assert int(out[cname]) == ctypes.sizeof(cls), cname
+        for fname, *_ in cls._fields_:
+            assert int(out[f"{cname}.{fname}"]) == getattr(cls, fname).offset, (cname, fname)

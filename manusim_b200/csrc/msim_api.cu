@@ -151,7 +151,7 @@ extern "C" int msim_create(const msim_tables_t* t, msim_handle_t* out) {
     L.scal = take((int)sizeof(Scal), 8);
     L.slab_bytes = align_up(off, 16);
 
-    // ---- block-shared table blob
+    // ---- scenario table blob (carried in the kernel parameters)
     std::vector<unsigned char> blob;
     auto put = [&](const void* src, size_t bytes, size_t align) {
         size_t o = (blob.size() + align - 1) / align * align;

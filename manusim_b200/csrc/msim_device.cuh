@@ -11,7 +11,7 @@ constexpr int kStageFlushAt = 25;  // a single event emits at most 7 records
 constexpr uint32_t kNone = 0xFFu;
 constexpr int kTabMax = 12288;     // scenario tables travel in the kernel parameters (constant bank), not shared memory
 
-// device-side distribution entry (block-shared table)
+// device-side distribution entry (scenario table in the kernel parameters)
 struct DDist {
     double raw0;   // params[0] in float64 (constant batch = count * raw0, utils.py:83-84)
     float d0, d1;  // derived parameters rounded to float32 for the Philox samplers
@@ -52,7 +52,7 @@ struct Scal {
 };
 
 // byte offsets of every per-replication array inside the warp's shared-memory slab and of every table
-// inside the block-shared table blob.  Computed once per handle on the host.
+// inside the scenario table blob (KParams::tblob).  Computed once per handle on the host.
 struct Lay {
     int32_t R, P, S, NT, MP, MD, NQ, UQ, K;
     // per-replication slab
@@ -66,7 +66,7 @@ struct Lay {
     int32_t p_obh, p_obt, p_fgqh, p_fgqt;
     int32_t po_prod, po_done, po_next, po_loc, do_prod, do_next;
     int32_t scal, slab_bytes;
-    // block-shared tables
+    // scenario tables (offsets into KParams::tblob)
     int32_t t_route_start, t_step_res, t_step_dist, t_setup, t_tbf, t_ttr, t_freq, t_qty, t_due, t_shipbuf, t_ccrpt,
         t_bytes;
 };

@@ -48,6 +48,34 @@ def stats_from_moments(mom: np.ndarray) -> pd.DataFrame:
     return pd.DataFrame({"mean": mean, "std": np.sqrt(np.maximum(var, 0.0)), "size": n.astype(np.int64)})
 
 
+def experiment_stats_from_moments(mom: np.ndarray, ring_names, experiment: str = "", confidence: float = 0.95,
+                                  precision: float = 0.05) -> pd.DataFrame:
+    """Per-(variable,key) experiment statistics with the reference's columns and formulas
+    (`ExperimentMetrics.calculate_experiment_stats(aggregate_variables=False)` + `_calculate_stats`, metrics.py:837-919):
+    size, size_ideal, mean, sample std, t-critical value, half-width `error`, relative error, confidence interval --
+    computed from the allreduced {sum x, sum x^2, n} vector instead of from one CSV per run."""
+    from scipy import stats as sps
+
+    base = stats_from_moments(mom)
+    rows = []
+    for (variable, key), mean, std, size in zip(ring_names, base["mean"], base["std"], base["size"]):
+        size = int(size)
+        if size == 0:
+            mean = std = t_crit = error = error_p = ci_low = ci_high = n_size = np.nan
+        elif size < 2:
+            std = t_crit = error = error_p = ci_low = ci_high = n_size = np.nan
+        else:
+            t_crit = sps.t.ppf(1 - ((1 - confidence) / 2), size - 1)
+            error = t_crit * (std / np.sqrt(size))
+            error_p = (0.0 if mean == 0 else np.nan) if (mean == 0 or np.isnan(mean)) else error / mean
+            ci_low, ci_high = mean - error, mean + error
+            n_size = np.square(t_crit * std / (precision * mean)) if (mean != 0 and not np.isnan(mean)) else 0.0
+        rows.append({"experiment": experiment, "variable": variable, "key": key, "size": size, "size_ideal": n_size,
+                     "mean": mean, "std": std, "confidence": confidence, "precision": precision, "t_crit": t_crit,
+                     "error": error, "error_p": error_p, "ci_low": ci_low, "ci_high": ci_high})
+    return pd.DataFrame(rows)
+
+
 class ExperimentRunner:
     def __init__(self, simulation, number_of_runs: int, save_folder_path: Path = None, run_name: str = None,
                  save_logs: bool = True, seed: int = None, n_jobs: int = 1, simulation_factory=None,
@@ -149,8 +177,5 @@ class ExperimentRunner:
         with open(self.save_folder_path / "experiment_summary.yaml", "w") as f:
             yaml.dump(summary, f)
         pd.DataFrame(self.run_metas).to_csv(self.save_folder_path / "experiment_metadata.csv", index=False)
-        st = stats_from_moments(self.moments)
-        names = self.sim.tables.ring_names()
-        st.insert(0, "key", [k for _, k in names])
-        st.insert(0, "variable", [v for v, _ in names])
+        st = experiment_stats_from_moments(self.moments, self.sim.tables.ring_names(), self.save_folder_path.name)
         st.to_csv(self.save_folder_path / "experiment_stats_device.csv", index=False)

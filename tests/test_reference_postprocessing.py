@@ -65,6 +65,18 @@ def test_reference_experiment_metrics_reads_our_tree(tmp_path):
     st = stats_from_moments(mom)
     np.testing.assert_allclose(st["mean"][k], got.mean(), rtol=1e-12)
     np.testing.assert_allclose(st["std"][k], got.std(ddof=1), rtol=1e-9)
+    # per-key statistics with the reference's own columns / formulas, from the moment vector
+    from manusim_b200.experiment import experiment_stats_from_moments
+
+    ours = experiment_stats_from_moments(mom, names, tmp_path.name, 0.95, 0.05)
+    theirs = em.calculate_experiment_stats(0.95, 0.05, aggregate_variables=False)
+    cols = ["size", "size_ideal", "mean", "std", "confidence", "precision", "t_crit", "error", "error_p", "ci_low", "ci_high"]
+    assert list(ours.columns) == ["experiment", "variable", "key", *cols]
+    merged = theirs.merge(ours, on=["variable", "key"], suffixes=("_ref", "_dev"))
+    assert len(merged) >= 160
+    for c in cols:
+        np.testing.assert_allclose(merged[c + "_dev"].to_numpy(dtype=float), merged[c + "_ref"].to_numpy(dtype=float),
+                                   rtol=1e-7, atol=1e-12, equal_nan=True, err_msg=c)
     # the reference can also read the raw logs we saved
     em.read_logs(["utilization"])
     assert len(em.logs) > 0 and set(em.logs["variable"]) == {"utilization"}

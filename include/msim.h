@@ -191,6 +191,13 @@ int msim_run_host(msim_handle_t h, const msim_host_args_t* args);
 int msim_reduce_metrics(msim_handle_t h, const double* acc_sum, const uint32_t* acc_cnt, const int32_t* status,
                         int64_t n_reps, double* out, void* stream);
 
+/* Per-VARIABLE statistics, the default of ExperimentMetrics.calculate_experiment_stats (metrics.py:809-816): per
+ * replication the per-key values of a variable are averaged over its keys (NaN-skipping) before the reduction over
+ * replications.  out is [18][3] float64 {sum, sum^2, n} in enum order (11 product, 4 resource, 3 general metrics),
+ * ACCUMULATED into. */
+int msim_reduce_variables(msim_handle_t h, const double* acc_sum, const uint32_t* acc_cnt, const int32_t* status,
+                          int64_t n_reps, double* out, void* stream);
+
 /* test hook: Philox4x32-10 blocks computed on the device; ctr [n][4], key [n][2], out [n][4] (HOST buffers) */
 int msim_test_philox(const uint32_t* ctr, const uint32_t* key, uint32_t* out, int64_t n);
 /* test hook: device variates; draws n values of `dist` with Philox key `seed` on stream id `stream_id`,

@@ -9,7 +9,7 @@ PKG = Path(__file__).resolve().parent
 LIB_PATH = PKG / "libmsim.so"
 
 EXPORTS = ["msim_version", "msim_last_error", "msim_create", "msim_destroy", "msim_query", "msim_run",
-           "msim_run_host", "msim_reduce_metrics", "msim_test_philox", "msim_test_variates"]
+           "msim_run_host", "msim_reduce_metrics", "msim_reduce_variables", "msim_test_philox", "msim_test_variates"]
 
 
 class Dist(C.Structure):
@@ -89,6 +89,8 @@ def load():
     lib.msim_run_host.argtypes = [C.c_void_p, C.POINTER(HostArgs)]
     lib.msim_reduce_metrics.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p,
                                         C.c_void_p]
+    lib.msim_reduce_variables.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p,
+                                          C.c_void_p]
     lib.msim_test_philox.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64]
     lib.msim_test_variates.argtypes = [C.POINTER(Dist), C.c_uint64, C.c_int32, C.c_int32, C.c_void_p, C.c_int64]
     for name in EXPORTS:

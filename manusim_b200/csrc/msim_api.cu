@@ -325,6 +325,15 @@ extern "C" int msim_reduce_metrics(msim_handle_t h, const double* acc_sum, const
     return 0;
 }
 
+extern "C" int msim_reduce_variables(msim_handle_t h, const double* acc_sum, const uint32_t* acc_cnt, const int32_t* status,
+                                     int64_t n_reps, double* out, void* stream) {
+    if (!h || !acc_sum || !acc_cnt || !status || !out) return fail(MSIM_E_INVALID, "null argument");
+    const Lay& L = h->kp.lay;
+    int rc = launch_reduce_variables(acc_sum, acc_cnt, status, n_reps, L.K, L.P, L.R, h->span, out, stream);
+    if (rc != 0) return fail(rc, "reduce launch failed");
+    return 0;
+}
+
 // ---------------------------------------------------------------------------------------------------------
 // host-buffer path: stage inputs, run, copy results back (the e2e leg of bench.py and the ctypes default)
 extern "C" int msim_run_host(msim_handle_t h, const msim_host_args_t* a) {

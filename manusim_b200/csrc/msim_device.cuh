@@ -90,6 +90,8 @@ int launch_sim(const KParams& p, int policy, int rng_mode, int grid, int block, 
 int sim_kernel_attrs(int policy, int rng_mode, size_t smem, int* regs, int block, int* blocks_per_sm);
 int launch_reduce(const double* acc_sum, const uint32_t* acc_cnt, const int32_t* status, int64_t n_reps, int K, int P,
                   int R, double span, double* out, void* stream);
+int launch_reduce_variables(const double* acc_sum, const uint32_t* acc_cnt, const int32_t* status, int64_t n_reps, int K,
+                            int P, int R, double span, double* out, void* stream);
 int launch_test_philox(const uint32_t* ctr, const uint32_t* key, uint32_t* out, int64_t n);
 int launch_test_variates(DDist d, uint64_t seed, int stream_id, int batch_count, double* out, int64_t n);
 DDist make_ddist(const msim_dist_t& d);

@@ -1294,6 +1294,53 @@ __global__ void reduce_kernel(const double* __restrict__ acc_sum, const uint32_t
     }
 }
 
+// per-VARIABLE experiment statistics (ExperimentMetrics' default, metrics.py:809-816): per replication the per-key
+// metric values are first averaged over the keys (NaN-skipping), then reduced to {sum, sum^2, n} over replications
+__global__ void reduce_variables_kernel(const double* __restrict__ acc_sum, const uint32_t* __restrict__ acc_cnt,
+                                        const int32_t* __restrict__ status, long long n_reps, int K, int P, int R,
+                                        double span, double* __restrict__ out) {
+    const int var = blockIdx.x;                      // 0..10 product metrics, 11..14 resource metrics, 15..17 general
+    int start, count, cls;
+    if (var < 11) { start = var * P; count = P; cls = var < 3 ? 0 : 2; }
+    else if (var < 15) { start = 11 * P + (var - 11) * R; count = R; cls = var < 14 ? 1 : 2; }
+    else { start = 11 * P + 4 * R + (var - 15); count = 1; cls = 2; }
+    double s1 = 0.0, s2 = 0.0, nn = 0.0;
+    for (long long i = threadIdx.x; i < n_reps; i += blockDim.x) {
+        if (status[i] != 0) continue;
+        double tot = 0.0;
+        int valid = 0;
+        for (int k = 0; k < count; ++k) {
+            double s = acc_sum[i * K + start + k];
+            uint32_t c = acc_cnt[i * K + start + k];
+            if (cls == 0) { tot += s; valid++; }
+            else if (cls == 1) { tot += s / span; valid++; }
+            else if (c) { tot += s / (double)c; valid++; }
+        }
+        if (!valid) continue;
+        double x = tot / (double)valid;
+        s1 += x; s2 += x * x; nn += 1.0;
+    }
+    __shared__ double sh[3][32];
+    for (int off = 16; off > 0; off >>= 1) {
+        s1 += __shfl_xor_sync(FULLMASK, s1, off);
+        s2 += __shfl_xor_sync(FULLMASK, s2, off);
+        nn += __shfl_xor_sync(FULLMASK, nn, off);
+    }
+    int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+    if (l == 0) { sh[0][w] = s1; sh[1][w] = s2; sh[2][w] = nn; }
+    __syncthreads();
+    if (w == 0) {
+        int nw = blockDim.x >> 5;
+        s1 = l < nw ? sh[0][l] : 0.0; s2 = l < nw ? sh[1][l] : 0.0; nn = l < nw ? sh[2][l] : 0.0;
+        for (int off = 16; off > 0; off >>= 1) {
+            s1 += __shfl_xor_sync(FULLMASK, s1, off);
+            s2 += __shfl_xor_sync(FULLMASK, s2, off);
+            nn += __shfl_xor_sync(FULLMASK, nn, off);
+        }
+        if (l == 0) { out[var * 3 + 0] += s1; out[var * 3 + 1] += s2; out[var * 3 + 2] += nn; }
+    }
+}
+
 __global__ void test_philox_kernel(const uint32_t* ctr, const uint32_t* key, uint32_t* out, long long n) {
     long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
     if (i >= n) return;
@@ -1374,6 +1421,12 @@ int launch_sim(const KParams& p, int policy, int rng_mode, int grid, int block, 
 int launch_reduce(const double* acc_sum, const uint32_t* acc_cnt, const int32_t* status, int64_t n_reps, int K, int P,
                   int R, double span, double* out, void* stream) {
     reduce_kernel<<<K, 256, 0, (cudaStream_t)stream>>>(acc_sum, acc_cnt, status, n_reps, K, P, R, span, out);
+    return cudaGetLastError() == cudaSuccess ? 0 : MSIM_E_CUDA;
+}
+
+int launch_reduce_variables(const double* acc_sum, const uint32_t* acc_cnt, const int32_t* status, int64_t n_reps, int K,
+                            int P, int R, double span, double* out, void* stream) {
+    reduce_variables_kernel<<<18, 256, 0, (cudaStream_t)stream>>>(acc_sum, acc_cnt, status, n_reps, K, P, R, span, out);
     return cudaGetLastError() == cudaSuccess ? 0 : MSIM_E_CUDA;
 }
 

@@ -259,6 +259,18 @@ class BatchEngine:
                                                     s.cuda_stream))
         return out
 
+    def reduce_variables(self, res: BatchResult, out=None, stream=None):
+        """Per-variable {sum x, sum x^2, n} with x = the replication's mean over the variable's keys -> [18,3]."""
+        torch = self.torch
+        if out is None:
+            out = torch.zeros((18, 3), dtype=torch.float64, device=self.device)
+        s = stream if stream is not None else torch.cuda.current_stream(self.device)
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.msim_reduce_variables(self.handle, res.acc_sum.data_ptr(), res.acc_cnt.data_ptr(),
+                                                      res.status.data_ptr(), res.acc_sum.shape[0], out.data_ptr(),
+                                                      s.cuda_stream))
+        return out
+
     # ------------------------------------------------------------------ host-buffer path (end to end)
     def alloc_host(self, n_reps: int, n_log_reps: int = 0, log_cap: int = 0) -> BatchResult:
         torch = self.torch

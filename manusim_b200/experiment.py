@@ -76,6 +76,16 @@ def experiment_stats_from_moments(mom: np.ndarray, ring_names, experiment: str =
     return pd.DataFrame(rows)
 
 
+def variable_stats_from_moments(mom18: np.ndarray, experiment: str = "", confidence: float = 0.95,
+                                precision: float = 0.05) -> pd.DataFrame:
+    """`experiment_stats.csv` as the reference writes it by default (one row per variable: per run the per-key values
+    are first averaged over the keys, metrics.py:809-835), from the [18,3] vector of `msim_reduce_variables`."""
+    from .compiler import GENERAL_METRICS, PRODUCT_METRICS, RESOURCE_METRICS
+
+    names = [(v, "") for v in (*PRODUCT_METRICS, *RESOURCE_METRICS, *GENERAL_METRICS)]
+    return experiment_stats_from_moments(mom18, names, experiment, confidence, precision).drop(columns=["key"])
+
+
 class ExperimentRunner:
     def __init__(self, simulation, number_of_runs: int, save_folder_path: Path = None, run_name: str = None,
                  save_logs: bool = True, seed: int = None, n_jobs: int = 1, simulation_factory=None,
@@ -129,11 +139,14 @@ class ExperimentRunner:
         res = eng.run(n, rep_seeds=keys, rep_offset=lo, n_log_reps=n_log, log_cap=self.log_capacity if n_log else 0)
         eng.retry_overflow(res, rep_seeds=keys)
         mom = eng.reduce(res)
+        mom_var = eng.reduce_variables(res)
         if world > 1:
             dist.all_reduce(mom)
+            dist.all_reduce(mom_var)
         torch.cuda.synchronize(eng.device)
         batch_time = time.time() - start
         self.moments = mom.cpu().numpy()
+        self.variable_moments = mom_var.cpu().numpy()
         status = res.status.cpu().numpy()
         acc_sum = res.acc_sum[:n_mat].cpu().numpy() if n_mat else np.zeros((0, eng.K))
         acc_cnt = res.acc_cnt[:n_mat].cpu().numpy() if n_mat else np.zeros((0, eng.K), dtype=np.int32)
@@ -179,3 +192,5 @@ class ExperimentRunner:
         pd.DataFrame(self.run_metas).to_csv(self.save_folder_path / "experiment_metadata.csv", index=False)
         st = experiment_stats_from_moments(self.moments, self.sim.tables.ring_names(), self.save_folder_path.name)
         st.to_csv(self.save_folder_path / "experiment_stats_device.csv", index=False)
+        variable_stats_from_moments(self.variable_moments, self.save_folder_path.name).to_csv(
+            self.save_folder_path / "experiment_stats_device_variables.csv", index=False)

@@ -303,3 +303,39 @@ def test_dbr_simulation_dropin_replays_reference_run():
     gotp = sim.products_metrics()
     for col in ("deliveredOntime", "lostSales", "flowTime", "released"):
         np.testing.assert_allclose(gotp[col].to_numpy(dtype=float), refp[col].to_numpy(dtype=float), rtol=1e-6, equal_nan=True)
+
+
+def test_device_variable_moments_equal_host_computation(tmp_path):
+    """msim_reduce_variables (per run: mean over the variable's keys, then sum / sum^2 / n over runs) against numpy on the
+    same accumulators; the runner writes the reference-format per-variable statistics file from it."""
+    import torch
+
+    from manusim_b200 import scenarios
+    from manusim_b200.experiment import ExperimentRunner
+    from manusim_b200.factory_sim import NewSimulation
+    from manusim_b200.metrics import metric_values
+
+    sim_cfg, res, prod, exp = scenarios.load_example("simple_scheduler")
+    cfg = dict(sim_cfg, run_until=300, memory_size=5000)
+    sim = NewSimulation(cfg, res, prod, print_mode="none")
+    eng, t = sim.engine, sim.tables
+    r = eng.run(37, seed=4)
+    mv = eng.reduce_variables(r)
+    torch.cuda.synchronize()
+    vals = metric_values(r.acc_sum.cpu().numpy(), r.acc_cnt.cpu().numpy(), t, 250.0)
+    P, R = t.P, t.R
+    groups = [slice(m * P, (m + 1) * P) for m in range(11)] + [slice(11 * P + m * R, 11 * P + (m + 1) * R) for m in range(4)] \
+        + [slice(11 * P + 4 * R + g, 11 * P + 4 * R + g + 1) for g in range(3)]
+    import warnings
+
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        xv = np.stack([np.nanmean(vals[:, g], axis=1) for g in groups], axis=1)
+    ok = ~np.isnan(xv)
+    want = np.stack([np.where(ok, xv, 0).sum(0), np.where(ok, xv ** 2, 0).sum(0), ok.sum(0).astype(float)], axis=1)
+    np.testing.assert_allclose(mv.cpu().numpy(), want, rtol=1e-12, atol=1e-12)
+    runner = ExperimentRunner(sim, number_of_runs=5, save_folder_path=tmp_path, save_logs=False, seed=123)
+    runner.run_experiment()
+    st = pd.read_csv(tmp_path / "experiment_stats_device_variables.csv")
+    assert list(st["variable"])[:3] == ["deliveredOntime", "deliveredLate", "lostSales"] and len(st) == 18
+    assert st["size"].between(0, 5).all() and (st["size"] == 5).sum() >= 10

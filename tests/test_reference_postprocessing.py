@@ -77,6 +77,24 @@ def test_reference_experiment_metrics_reads_our_tree(tmp_path):
     for c in cols:
         np.testing.assert_allclose(merged[c + "_dev"].to_numpy(dtype=float), merged[c + "_ref"].to_numpy(dtype=float),
                                    rtol=1e-7, atol=1e-12, equal_nan=True, err_msg=c)
+    # per-variable statistics (the reference's default experiment_stats.csv): per run mean over keys, then over runs
+    from manusim_b200.experiment import variable_stats_from_moments
+
+    P, R = t.P, t.R
+    groups = [slice(m * P, (m + 1) * P) for m in range(11)] + [slice(11 * P + m * R, 11 * P + (m + 1) * R) for m in range(4)] \
+        + [slice(11 * P + 4 * R + g, 11 * P + 4 * R + g + 1) for g in range(3)]
+    with np.errstate(invalid="ignore"), __import__("warnings").catch_warnings():
+        __import__("warnings").simplefilter("ignore")
+        xv = np.stack([np.nanmean(vals[:, g], axis=1) for g in groups], axis=1)          # [runs, 18]
+    okv = ~np.isnan(xv)
+    mom18 = np.stack([np.where(okv, xv, 0).sum(0), np.where(okv, xv ** 2, 0).sum(0), okv.sum(0).astype(float)], axis=1)
+    ours_v = variable_stats_from_moments(mom18, tmp_path.name, 0.95, 0.05)
+    theirs_v = stats[stats.variable.isin(ours_v.variable)]
+    mv = theirs_v.merge(ours_v, on="variable", suffixes=("_ref", "_dev"))
+    assert len(mv) == 18
+    for c in cols:
+        np.testing.assert_allclose(mv[c + "_dev"].to_numpy(dtype=float), mv[c + "_ref"].to_numpy(dtype=float),
+                                   rtol=1e-7, atol=1e-12, equal_nan=True, err_msg=c)
     # the reference can also read the raw logs we saved
     em.read_logs(["utilization"])
     assert len(em.logs) > 0 and set(em.logs["variable"]) == {"utilization"}

@@ -34,6 +34,14 @@ namespace msim {
 
 #define FULLMASK 0xFFFFFFFFu
 
+// Launch syntax and the dynamic shared-memory declaration go through two macros so that the host-side SIMT emulator
+// under tests/emu (test infrastructure: runs THIS source on CPU fibers for sanitizer and parity checks, never part of
+// the product) can substitute its own.
+#ifndef MSIM_LAUNCH
+#define MSIM_LAUNCH(kernel, grid, block, smem, stream, ...) kernel<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__)
+#define MSIM_DYN_SMEM(name) extern __shared__ __align__(16) unsigned char name[]
+#endif
+
 enum Op : uint32_t {
     OP_NONE = 0,
     OP_TO_WARMUP, OP_TO_DEMAND, OP_PUT_INBOUND, OP_SCHED_GOT, OP_PUT_OUTBOUND,
@@ -1003,7 +1011,7 @@ __device__ __forceinline__ void warp_flush(const KParams& p, const unsigned char
 // ---------------------------------------------------------------------------------------------------------
 template <int POLICY, int RNG>
 __global__ void __launch_bounds__(256, 5) sim_kernel(const __grid_constant__ KParams p) {
-    extern __shared__ __align__(16) unsigned char smem[];
+    MSIM_DYN_SMEM(smem);
     const Lay& L = p.lay;
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
@@ -1414,29 +1422,29 @@ int launch_sim(const KParams& p, int policy, int rng_mode, int grid, int block, 
         if (cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return MSIM_E_CUDA;
         smem_set[policy][rng_mode] = smem;
     }
-    f<<<grid, block, smem, (cudaStream_t)stream>>>(p);
+    MSIM_LAUNCH(f, grid, block, smem, (cudaStream_t)stream, p);
     return cudaGetLastError() == cudaSuccess ? 0 : MSIM_E_CUDA;
 }
 
 int launch_reduce(const double* acc_sum, const uint32_t* acc_cnt, const int32_t* status, int64_t n_reps, int K, int P,
                   int R, double span, double* out, void* stream) {
-    reduce_kernel<<<K, 256, 0, (cudaStream_t)stream>>>(acc_sum, acc_cnt, status, n_reps, K, P, R, span, out);
+    MSIM_LAUNCH(reduce_kernel, K, 256, 0, (cudaStream_t)stream, acc_sum, acc_cnt, status, n_reps, K, P, R, span, out);
     return cudaGetLastError() == cudaSuccess ? 0 : MSIM_E_CUDA;
 }
 
 int launch_reduce_variables(const double* acc_sum, const uint32_t* acc_cnt, const int32_t* status, int64_t n_reps, int K,
                             int P, int R, double span, double* out, void* stream) {
-    reduce_variables_kernel<<<18, 256, 0, (cudaStream_t)stream>>>(acc_sum, acc_cnt, status, n_reps, K, P, R, span, out);
+    MSIM_LAUNCH(reduce_variables_kernel, 18, 256, 0, (cudaStream_t)stream, acc_sum, acc_cnt, status, n_reps, K, P, R, span, out);
     return cudaGetLastError() == cudaSuccess ? 0 : MSIM_E_CUDA;
 }
 
 int launch_test_philox(const uint32_t* ctr, const uint32_t* key, uint32_t* out, int64_t n) {
-    test_philox_kernel<<<(unsigned)((n + 127) / 128), 128>>>(ctr, key, out, n);
+    MSIM_LAUNCH(test_philox_kernel, (unsigned)((n + 127) / 128), 128, 0, (cudaStream_t)0, ctr, key, out, n);
     return cudaGetLastError() == cudaSuccess ? 0 : MSIM_E_CUDA;
 }
 
 int launch_test_variates(DDist d, uint64_t seed, int stream_id, int batch_count, double* out, int64_t n) {
-    test_variates_kernel<<<(unsigned)((n + 127) / 128), 128>>>(d, seed, stream_id, batch_count, out, n);
+    MSIM_LAUNCH(test_variates_kernel, (unsigned)((n + 127) / 128), 128, 0, (cudaStream_t)0, d, seed, stream_id, batch_count, out, n);
     return cudaGetLastError() == cudaSuccess ? 0 : MSIM_E_CUDA;
 }
 

@@ -56,6 +56,40 @@ def pack_tapes(tapes: Sequence[Dict[str, np.ndarray]]):
     return out
 
 
+def make_ctables(t: ScenarioTables):
+    """ScenarioTables -> (msim_tables_t, list of the numpy/ctypes arrays its pointers refer to)."""
+    keep = []
+    ct = _lib.Tables()
+    ct.n_resources, ct.n_products, ct.n_steps = t.R, t.P, int(t.route_start[-1])
+    rs = np.ascontiguousarray(t.route_start, dtype=np.int32)
+    sr = np.ascontiguousarray(t.step_resource, dtype=np.int32)
+    sb = np.ascontiguousarray(t.shipping_buffer, dtype=np.float64)
+    keep += [rs, sr, sb]
+    ct.route_start = rs.ctypes.data_as(C.POINTER(C.c_int32))
+    ct.step_resource = sr.ctypes.data_as(C.POINTER(C.c_int32))
+    ct.prod_shipping_buffer = sb.ctypes.data_as(C.POINTER(C.c_double))
+    for name in ("step_time", "res_setup", "res_tbf", "res_ttr", "prod_freq", "prod_qty", "prod_due"):
+        arr = _dist_array(getattr(t, name))
+        keep.append(arr)
+        setattr(ct, name, arr)
+    ct.run_until, ct.warmup = float(t.run_until), float(t.warmup)
+    ct.run_until_is_int, ct.warmup_is_int = int(isinstance(t.run_until, int)), int(isinstance(t.warmup, int))
+    ct.delivery_mode, ct.policy, ct.log_queues = t.delivery_mode, t.policy, int(t.log_queues)
+    if t.dbr:
+        d = t.dbr
+        cpt = np.ascontiguousarray(d["ccr_pt"], dtype=np.float64)
+        keep.append(cpt)
+        ct.dbr_ccr, ct.dbr_repair = d["ccr"], int(d["repair"])
+        ct.dbr_interval_is_int = int(isinstance(d["interval"], int))
+        ct.dbr_interval, ct.dbr_cb_target = float(d["interval"]), d["cb_target"]
+        ct.dbr_release_limit, ct.dbr_ccr_limit = d["release_limit"], d["ccr_limit"]
+        ct.dbr_min_lot, ct.dbr_ccr_setup = d["min_lot"], d["ccr_setup"]
+        ct.dbr_ccr_pt = cpt.ctypes.data_as(C.POINTER(C.c_double))
+    ct.max_production_orders, ct.max_demand_orders = t.max_production_orders, t.max_demand_orders
+    ct.fifo_capacity = t.fifo_capacity
+    return ct, keep
+
+
 @dataclass
 class BatchResult:
     acc_sum: "object"       # [n, K] float64
@@ -81,36 +115,7 @@ class BatchEngine:
         self.lib = _lib.load()
         self.device = torch.device("cuda", torch.cuda.current_device() if device is None else device)
         self.tables = tables
-        t = tables
-        self._keep = []
-        ct = _lib.Tables()
-        ct.n_resources, ct.n_products, ct.n_steps = t.R, t.P, int(t.route_start[-1])
-        rs = np.ascontiguousarray(t.route_start, dtype=np.int32)
-        sr = np.ascontiguousarray(t.step_resource, dtype=np.int32)
-        sb = np.ascontiguousarray(t.shipping_buffer, dtype=np.float64)
-        self._keep += [rs, sr, sb]
-        ct.route_start = rs.ctypes.data_as(C.POINTER(C.c_int32))
-        ct.step_resource = sr.ctypes.data_as(C.POINTER(C.c_int32))
-        ct.prod_shipping_buffer = sb.ctypes.data_as(C.POINTER(C.c_double))
-        for name in ("step_time", "res_setup", "res_tbf", "res_ttr", "prod_freq", "prod_qty", "prod_due"):
-            arr = _dist_array(getattr(t, name))
-            self._keep.append(arr)
-            setattr(ct, name, arr)
-        ct.run_until, ct.warmup = float(t.run_until), float(t.warmup)
-        ct.run_until_is_int, ct.warmup_is_int = int(isinstance(t.run_until, int)), int(isinstance(t.warmup, int))
-        ct.delivery_mode, ct.policy, ct.log_queues = t.delivery_mode, t.policy, int(t.log_queues)
-        if t.dbr:
-            d = t.dbr
-            cpt = np.ascontiguousarray(d["ccr_pt"], dtype=np.float64)
-            self._keep.append(cpt)
-            ct.dbr_ccr, ct.dbr_repair = d["ccr"], int(d["repair"])
-            ct.dbr_interval_is_int = int(isinstance(d["interval"], int))
-            ct.dbr_interval, ct.dbr_cb_target = float(d["interval"]), d["cb_target"]
-            ct.dbr_release_limit, ct.dbr_ccr_limit = d["release_limit"], d["ccr_limit"]
-            ct.dbr_min_lot, ct.dbr_ccr_setup = d["min_lot"], d["ccr_setup"]
-            ct.dbr_ccr_pt = cpt.ctypes.data_as(C.POINTER(C.c_double))
-        ct.max_production_orders, ct.max_demand_orders = t.max_production_orders, t.max_demand_orders
-        ct.fifo_capacity = t.fifo_capacity
+        ct, self._keep = make_ctables(tables)
         self.handle = C.c_void_p()
         with torch.cuda.device(self.device):
             _lib.check(self.lib.msim_create(C.byref(ct), C.byref(self.handle)))

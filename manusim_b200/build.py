@@ -9,7 +9,7 @@ from pathlib import Path
 PKG = Path(__file__).resolve().parent
 CSRC = PKG / "csrc"
 LIB = PKG / "libmsim.so"
-SOURCES = ["msim_kernel.cu", "msim_api.cu"]
+SOURCES = ["msim_kernel.cu", "msim_kernel_aos.cu", "msim_api.cu"]
 HEADERS = ["msim_device.cuh", "philox.cuh", "../../include/msim.h"]
 
 
@@ -29,16 +29,31 @@ def needs_build() -> bool:
 
 
 def build_lib(force: bool = False, verbose: bool = False) -> Path:
+    """One nvcc per translation unit (in parallel), then one link: libmsim.so holds the default kernel
+    (msim_kernel.cu), its experimental array-of-structures twin (msim_kernel_aos.cu) and the C ABI (msim_api.cu)."""
     if not force and not needs_build():
         return LIB
-    cmd = [_nvcc(), "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
-           "-shared", "-Xcompiler", "-fPIC", "-Xptxas", "-v" if verbose else "-O3",
-           "-o", str(LIB)] + [str(CSRC / s) for s in SOURCES]
-    res = subprocess.run(cmd, capture_output=True, text=True)
+    nvcc = _nvcc()
+    flags = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC",
+             "-Xptxas", "-v" if verbose else "-O3"]
+    objdir = PKG / "build"
+    objdir.mkdir(exist_ok=True)
+    objs, procs = [], []
+    for s in SOURCES:
+        o = objdir / (Path(s).stem + ".o")
+        objs.append(str(o))
+        procs.append(subprocess.Popen([nvcc] + flags + ["-c", str(CSRC / s), "-o", str(o)], stdout=subprocess.PIPE,
+                                      stderr=subprocess.PIPE, text=True))
+    outs = [p.communicate() for p in procs]
     if verbose:
-        sys.stderr.write(res.stderr)
+        for _, err in outs:
+            sys.stderr.write(err)
+    if any(p.returncode != 0 for p in procs):
+        raise RuntimeError("nvcc failed:\n" + "\n".join(o + e for o, e in outs))
+    res = subprocess.run([nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", str(LIB)] + objs,
+                         capture_output=True, text=True)
     if res.returncode != 0:
-        raise RuntimeError(f"nvcc failed:\n{res.stdout}\n{res.stderr}")
+        raise RuntimeError(f"nvcc link failed:\n{res.stdout}\n{res.stderr}")
     return LIB
 
 

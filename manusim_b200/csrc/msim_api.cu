@@ -7,6 +7,7 @@
 #include <cuda_runtime.h>
 #include <math.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 #include <string>
 #include <vector>
@@ -25,6 +26,7 @@ static int fail(int code, const std::string& msg) { g_err = msg; return code; }
 struct msim_handle_s {
     KParams kp;                 // layout + scalar parameters (args filled per run)
     int policy;
+    int aos;                    // 1: array-of-structures slab + msim::aos kernels (experimental, MSIM_SLAB_LAYOUT=aos)
     int n_sms;
     int warps_per_block[2];     // per rng mode (the Philox and replay kernels differ in register use)
     int blocks_per_sm[2];
@@ -106,6 +108,11 @@ extern "C" int msim_create(const msim_tables_t* t, msim_handle_t* out) {
     msim_handle_s* h = new msim_handle_s();
     memset(&h->kp, 0, sizeof(h->kp));
     h->policy = t->policy;
+    {
+        const char* lay = getenv("MSIM_SLAB_LAYOUT");       // read per handle; default = the measured SoA kernel
+        h->aos = lay && strcmp(lay, "aos") == 0;
+        if (lay && !h->aos && strcmp(lay, "soa") != 0) { delete h; return fail(MSIM_E_INVALID, "MSIM_SLAB_LAYOUT must be soa or aos"); }
+    }
     h->d_scratch = nullptr; h->scratch_bytes = 0;
     Lay& L = h->kp.lay;
     L.R = R; L.P = P; L.S = S;
@@ -123,31 +130,52 @@ extern "C" int msim_create(const msim_tables_t* t, msim_handle_t* out) {
     // ---- per-replication slab layout
     int off = 0;
     auto take = [&](int bytes, int align) { off = align_up(off, align); int o = off; off += bytes; return o; };
-    L.stage = take(kStageCap * 16, 16);
-    L.nq = take(L.NQ * 4, 4);
-    L.uq = take(L.UQ * 4, 4);
-    L.tm_time = take(L.NT * 4, 4);
-    L.tm_eid = take(L.NT * 4, 4);
-    L.tm_ev = take(L.NT * 4, 4);
-    L.rb = take(2 * 16 * 8, 8);                 // precomputed (x,u) pairs of streams B,C (philox.cuh kXuBuf)
-    L.r_tpy = dbr ? take(R * 8, 8) : 0; L.r_start_d = dbr ? take(R * 8, 8) : 0; L.r_utf_d = dbr ? take(R * 8, 8) : 0;
-    L.r_utf = take(R * 4, 4); L.r_tbf = take(R * 4, 4); L.r_setup = take(R * 4, 4); L.r_start = take(R * 4, 4);
-    L.r_busy = take(R * 4, 4);
-    L.r_qq = t->log_queues ? take(R * 4, 4) : 0; L.r_lastq = t->log_queues ? take(R * 4, 4) : 0;   // `queue` records only
-    L.p_fg = take(P * 4, 4); L.p_wip = take(P * 4, 4); L.p_fgc = take(P * 4, 4); L.p_dqty = take(P * 4, 4);
-    L.p_ddue = take(P * 4, 4);
-    L.po_rel = take(L.MP * 4, 4); L.po_qty = take(L.MP * 4, 4);
-    L.po_prio = prio ? take(L.MP * 4, 4) : 0;
-    L.po_tt = dbr ? take(L.MP * 4, 4) : 0; L.po_eid = dbr ? take(L.MP * 4, 4) : 0; L.po_ccr = dbr ? take(L.MP * 4, 4) : 0;
-    L.do_arr = take(L.MD * 4, 4); L.do_due = take(L.MD * 4, 4); L.do_qty = take(L.MD * 4, 4);
-    L.do_tt = on_due ? take(L.MD * 4, 4) : 0;  // delivery timers exist only in onDue mode
-    L.do_eid = on_due ? take(L.MD * 4, 4) : 0;
-    L.r_flags = dbr ? take(R, 1) : 0; L.po_relpy = dbr ? take(L.MP, 1) : 0;
-    L.r_cur = take(R, 1); L.r_tcur = take(R, 1);
-    L.r_inh = take(R, 1); L.r_int = take(R, 1); L.r_outh = take(R, 1); L.r_outt = take(R, 1);
-    L.p_obh = take(P, 1); L.p_obt = take(P, 1); L.p_fgqh = take(P, 1); L.p_fgqt = take(P, 1);
-    L.po_prod = take(L.MP, 1); L.po_done = take(L.MP, 1); L.po_next = take(L.MP, 1); L.po_loc = take(L.MP, 1);
-    L.do_prod = take(L.MD, 1); L.do_next = take(L.MD, 1);
+    if (h->aos) {
+        // struct arrays first (resources at slab offset 0, msim_kernel_aos.cu), then what the whole warp reads
+        L.r_utf = take(R * kAosResStride, 4);
+        L.p_fg = take(P * kAosPrdStride, 4);
+        L.po_rel = take(L.MP * aos_po_stride(t->policy), 4);
+        L.do_arr = take(L.MD * kAosDoStride, 4);
+        L.do_prod = take(L.MD * kAosDoLinkStride, 2);
+        L.stage = take(kStageCap * 16, 16);
+        L.nq = take(L.NQ * 4, 4);
+        L.uq = take(L.UQ * 4, 4);
+        L.tm_time = take(L.NT * 4, 4);
+        L.tm_eid = take(L.NT * 4, 4);
+        L.tm_ev = take(L.NT * 4, 4);
+        L.rb = take(2 * 16 * 8, 8);
+        L.r_tpy = dbr ? take(R * 8, 8) : 0; L.r_start_d = dbr ? take(R * 8, 8) : 0; L.r_utf_d = dbr ? take(R * 8, 8) : 0;
+        L.r_qq = t->log_queues ? take(R * 4, 4) : 0; L.r_lastq = t->log_queues ? take(R * 4, 4) : 0;
+        L.po_tt = dbr ? take(L.MP * 4, 4) : 0; L.po_eid = dbr ? take(L.MP * 4, 4) : 0;
+        L.do_tt = on_due ? take(L.MD * 4, 4) : 0; L.do_eid = on_due ? take(L.MD * 4, 4) : 0;
+        L.r_flags = dbr ? take(R, 1) : 0; L.po_relpy = dbr ? take(L.MP, 1) : 0;
+    } else {
+        L.stage = take(kStageCap * 16, 16);
+        L.nq = take(L.NQ * 4, 4);
+        L.uq = take(L.UQ * 4, 4);
+        L.tm_time = take(L.NT * 4, 4);
+        L.tm_eid = take(L.NT * 4, 4);
+        L.tm_ev = take(L.NT * 4, 4);
+        L.rb = take(2 * 16 * 8, 8);                 // precomputed (x,u) pairs of streams B,C (philox.cuh kXuBuf)
+        L.r_tpy = dbr ? take(R * 8, 8) : 0; L.r_start_d = dbr ? take(R * 8, 8) : 0; L.r_utf_d = dbr ? take(R * 8, 8) : 0;
+        L.r_utf = take(R * 4, 4); L.r_tbf = take(R * 4, 4); L.r_setup = take(R * 4, 4); L.r_start = take(R * 4, 4);
+        L.r_busy = take(R * 4, 4);
+        L.r_qq = t->log_queues ? take(R * 4, 4) : 0; L.r_lastq = t->log_queues ? take(R * 4, 4) : 0;   // `queue` records only
+        L.p_fg = take(P * 4, 4); L.p_wip = take(P * 4, 4); L.p_fgc = take(P * 4, 4); L.p_dqty = take(P * 4, 4);
+        L.p_ddue = take(P * 4, 4);
+        L.po_rel = take(L.MP * 4, 4); L.po_qty = take(L.MP * 4, 4);
+        L.po_prio = prio ? take(L.MP * 4, 4) : 0;
+        L.po_tt = dbr ? take(L.MP * 4, 4) : 0; L.po_eid = dbr ? take(L.MP * 4, 4) : 0; L.po_ccr = dbr ? take(L.MP * 4, 4) : 0;
+        L.do_arr = take(L.MD * 4, 4); L.do_due = take(L.MD * 4, 4); L.do_qty = take(L.MD * 4, 4);
+        L.do_tt = on_due ? take(L.MD * 4, 4) : 0;  // delivery timers exist only in onDue mode
+        L.do_eid = on_due ? take(L.MD * 4, 4) : 0;
+        L.r_flags = dbr ? take(R, 1) : 0; L.po_relpy = dbr ? take(L.MP, 1) : 0;
+        L.r_cur = take(R, 1); L.r_tcur = take(R, 1);
+        L.r_inh = take(R, 1); L.r_int = take(R, 1); L.r_outh = take(R, 1); L.r_outt = take(R, 1);
+        L.p_obh = take(P, 1); L.p_obt = take(P, 1); L.p_fgqh = take(P, 1); L.p_fgqt = take(P, 1);
+        L.po_prod = take(L.MP, 1); L.po_done = take(L.MP, 1); L.po_next = take(L.MP, 1); L.po_loc = take(L.MP, 1);
+        L.do_prod = take(L.MD, 1); L.do_next = take(L.MD, 1);
+    }
     L.scal = take((int)sizeof(Scal), 8);
     L.slab_bytes = align_up(off, 16);
 
@@ -239,7 +267,8 @@ extern "C" int msim_create(const msim_tables_t* t, msim_handle_t* out) {
             size_t need = (size_t)w * L.slab_bytes;
             if (need > smem_blk_max) break;
             int nblk = 0, regs = 0;
-            int rc = sim_kernel_attrs(h->policy, rng, need, &regs, w * 32, &nblk);
+            int rc = h->aos ? aos::sim_kernel_attrs(h->policy, rng, need, &regs, w * 32, &nblk)
+                            : sim_kernel_attrs(h->policy, rng, need, &regs, w * 32, &nblk);
             if (rc != 0) {
                 delete h;
                 return fail(rc, rc == MSIM_E_UNSUPPORTED ? "policy not available in this build" : "kernel attribute query failed");
@@ -311,7 +340,8 @@ extern "C" int msim_run(msim_handle_t h, const msim_run_args_t* a) {
     long long blocks_needed = (a->n_reps + wpb - 1) / wpb;
     long long grid = (long long)h->n_sms * h->blocks_per_sm[rng];
     if (grid > blocks_needed) grid = blocks_needed;
-    int rc = launch_sim(kp, h->policy, rng, (int)grid, wpb * 32, h->smem_bytes[rng], st);
+    int rc = h->aos ? aos::launch_sim(kp, h->policy, rng, (int)grid, wpb * 32, h->smem_bytes[rng], st)
+                    : launch_sim(kp, h->policy, rng, (int)grid, wpb * 32, h->smem_bytes[rng], st);
     if (rc != 0) return fail(rc, "simulation kernel launch failed (grid/block/shared-memory configuration)");
     return 0;
 }

@@ -85,6 +85,16 @@ struct KParams {
     msim_run_args_t a;             // device pointers
 };
 
+// array-of-structures slab of the experimental kernel twin (msim_kernel_aos.cu): struct strides in bytes.  In that
+// layout Lay::r_utf (= 0), p_fg, po_rel, do_arr and do_prod hold the start of the resource / product / production-
+// order / demand-order (floats; link bytes) struct arrays and the other per-field offsets of those entities are unused.
+constexpr int kAosResStride = 28, kAosPrdStride = 24, kAosDoStride = 12, kAosDoLinkStride = 2;
+__host__ __device__ constexpr int aos_po_stride(int policy) { return policy == MSIM_POLICY_FIFO ? 12 : 16; }   // + prio (PRIO/EDD) or ccr (DBR)
+namespace aos {
+int launch_sim(const KParams& p, int policy, int rng_mode, int grid, int block, size_t smem, void* stream);
+int sim_kernel_attrs(int policy, int rng_mode, size_t smem, int* regs, int block, int* blocks_per_sm);
+}
+
 // launchers implemented in msim_kernel.cu
 int launch_sim(const KParams& p, int policy, int rng_mode, int grid, int block, size_t smem, void* stream);
 int sim_kernel_attrs(int policy, int rng_mode, size_t smem, int* regs, int block, int* blocks_per_sm);

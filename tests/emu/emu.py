@@ -22,7 +22,7 @@ if str(ROOT) not in sys.path:
     sys.path.insert(0, str(ROOT))
 CSRC = ROOT / "manusim_b200" / "csrc"
 BUILD = HERE / "_build"
-SOURCES = [CSRC / "msim_kernel.cu", CSRC / "msim_api.cu", HERE / "emu_runtime.cpp"]
+SOURCES = [CSRC / "msim_kernel.cu", CSRC / "msim_kernel_aos.cu", CSRC / "msim_api.cu", HERE / "emu_runtime.cpp"]
 DEPS = SOURCES + [CSRC / "msim_device.cuh", CSRC / "philox.cuh", ROOT / "include" / "msim.h",
                   HERE / "include" / "cuda_runtime.h", HERE / "include" / "math_constants.h"]
 
@@ -30,6 +30,8 @@ FLAVOURS = {
     # -ffp-contract=off: the *_rn intrinsics are single IEEE operations (replay mode is bit-identical to the GPU)
     "plain": ["-O2", "-g"],
     # -O0 keeps the sanitizer build at ~20 s (eight kernel instantiations); the sanitizer runs use small scenarios
+    # line-execution counts of the kernel source (gcov) for tools/instr_model.py
+    "cov": ["-O0", "-g", "--coverage"],
     "asan": ["-O0", "-g", "-fsanitize=address,undefined", "-fno-sanitize-recover=undefined", "-fno-omit-frame-pointer"],
 }
 
@@ -85,7 +87,7 @@ def load(flavour: str = "plain"):
 class EmuEngine:
     """numpy twin of manusim_b200.engine.BatchEngine.run for the emulated library ("device" memory = host memory)."""
 
-    def __init__(self, tables, flavour: str = "plain"):
+    def __init__(self, tables, flavour: str = "plain", layout: str | None = None):
         from manusim_b200 import _lib as L
         from manusim_b200.engine import make_ctables
 
@@ -94,7 +96,17 @@ class EmuEngine:
         self.tables = tables
         ct, self._keep = make_ctables(tables)
         self.handle = C.c_void_p()
-        self._check(self.lib.msim_create(C.byref(ct), C.byref(self.handle)))
+        old = os.environ.get("MSIM_SLAB_LAYOUT")
+        if layout is not None:                      # read by msim_create, per handle
+            os.environ["MSIM_SLAB_LAYOUT"] = layout
+        try:
+            self._check(self.lib.msim_create(C.byref(ct), C.byref(self.handle)))
+        finally:
+            if layout is not None:
+                if old is None:
+                    os.environ.pop("MSIM_SLAB_LAYOUT", None)
+                else:
+                    os.environ["MSIM_SLAB_LAYOUT"] = old
         info = L.Info()
         self._check(self.lib.msim_query(self.handle, C.byref(info)))
         self.info = {f[0]: getattr(info, f[0]) for f in L.Info._fields_}

@@ -39,7 +39,7 @@
 #define __host__
 #define __global__
 #define __forceinline__ inline __attribute__((always_inline))
-#define __noinline__ __attribute__((noinline))
+#define __noinline__ __attribute__((noinline)) inline   // vague linkage: device functions live in headers shared by several .cu files
 #define __launch_bounds__(...)
 #define __grid_constant__
 #define __align__(n) __attribute__((aligned(n)))

@@ -62,7 +62,10 @@ def philox(policy, mode, repair=False, log_queues=False):
 def main():
     inject = "--inject" in sys.argv
     cases = 0
-    for wpb in () if inject else ("", "1"):
+    # (CTA shape, slab layout): the default kernel with the product's CTA shape and with one warp per CTA, then the
+    # experimental array-of-structures twin with one warp per CTA
+    for wpb, layout in () if inject else (("", "soa"), ("1", "soa"), ("1", "aos")):
+        os.environ["MSIM_SLAB_LAYOUT"] = layout
         if wpb:
             os.environ["MSIM_EMU_WPB"] = wpb
         else:
@@ -76,6 +79,7 @@ def main():
         philox("dbr", "instantly", repair=True)
         philox("dbr", "instantly", repair=False)
         cases += 2
+    os.environ.pop("MSIM_SLAB_LAYOUT", None)
     if inject:
         g = load_golden("toy2")
         scn = g["scenario"]

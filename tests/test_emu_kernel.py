@@ -37,20 +37,26 @@ def emu():
     return m
 
 
-def _engine(emu, scn, **kw):
+# "soa" = the default kernel (msim_kernel.cu); "aos" = its experimental array-of-structures twin (msim_kernel_aos.cu,
+# selected per handle with MSIM_SLAB_LAYOUT=aos)
+LAYOUTS = ["soa", "aos"]
+
+
+def _engine(emu, scn, layout=None, **kw):
     from manusim_b200 import compile_scenario
 
     t = compile_scenario(scn["cfg"], scn["resources"], scn["products"], policy=POLICY[scn["policy"]],
                          dbr_repair="P3" in scn["patches"], **kw)
-    return emu.EmuEngine(t)
+    return emu.EmuEngine(t, layout=layout)
 
 
+@pytest.mark.parametrize("layout", LAYOUTS)
 @pytest.mark.parametrize("name", GOLDEN_NAMES)
-def test_emulated_kernel_replays_reference_goldens_bit_exact(emu, name):
+def test_emulated_kernel_replays_reference_goldens_bit_exact(emu, name, layout):
     from manusim_b200.engine import decode_log
 
     g = load_golden(name)
-    eng = _engine(emu, g["scenario"])
+    eng = _engine(emu, g["scenario"], layout)
     n = 2
     res = eng.run(n, tapes=[{k: g["tape_" + k] for k in "ABCD"}] * n, n_log_reps=n, log_cap=len(g["ring"]) + 64)
     assert (res.status == 0).all(), res.status
@@ -71,12 +77,13 @@ def test_emulated_kernel_replays_reference_goldens_bit_exact(emu, name):
         assert np.array_equal(res.acc_cnt[i].astype(np.int64), c)
 
 
+@pytest.mark.parametrize("layout", LAYOUTS)
 @pytest.mark.parametrize("name,status", list(zip(ERROR_NAMES, (1, 2))))
-def test_emulated_kernel_value_error_cases(emu, name, status):
+def test_emulated_kernel_value_error_cases(emu, name, status, layout):
     from manusim_b200.engine import decode_log
 
     g = load_golden(name)
-    eng = _engine(emu, g["scenario"])
+    eng = _engine(emu, g["scenario"], layout)
     res = eng.run(2, tapes=[{k: g["tape_" + k] for k in "ABCD"}] * 2, n_log_reps=2, log_cap=4096)
     assert (res.status == status).all()
     ring, tm, val, _ = decode_log(res.log[1], int(res.log_count[1]))
@@ -84,8 +91,9 @@ def test_emulated_kernel_value_error_cases(emu, name, status):
     assert np.array_equal(tm, g["time"]) and np.array_equal(val, g["value"])
 
 
+@pytest.mark.parametrize("layout", LAYOUTS)
 @pytest.mark.parametrize("seed", list(range(48)) if FULL else list(range(0, 48, 4)))
-def test_emulated_kernel_random_scenarios_match_oracle(emu, seed):
+def test_emulated_kernel_random_scenarios_match_oracle(emu, seed, layout):
     """Same scenarios and the same check as tests/test_gpu_fuzz.py (every 4th seed unless MSIM_EMU_FULL=1)."""
     from test_gpu_fuzz import random_scenario
 
@@ -95,7 +103,7 @@ def test_emulated_kernel_random_scenarios_match_oracle(emu, seed):
 
     cfg, res, prod, policy, repair = random_scenario(seed)
     eng = emu.EmuEngine(compile_scenario(cfg, res, prod, policy=policy, dbr_repair=repair, max_production_orders=250,
-                                         max_demand_orders=250, fifo_capacity=256))
+                                         max_demand_orders=250, fifo_capacity=256), layout=layout)
     n = 3
     r = eng.run(n, seed=1000 + seed, n_log_reps=n, log_cap=1 << 16, record_tapes=1 << 14)
     cnt = r.rec["count"]
@@ -154,7 +162,7 @@ def test_kernel_source_is_clean_under_address_and_ub_sanitizers(emu):
     r = subprocess.run([sys.executable, script], env=env, capture_output=True, text=True, timeout=900)
     assert r.returncode == 0, r.stderr[-4000:]
     out = json.loads(r.stdout.strip().splitlines()[-1])
-    assert out["sanitize"] == "ok" and out["cases"] >= 20
+    assert out["sanitize"] == "ok" and out["cases"] >= 39
     assert "runtime error" not in r.stderr and "AddressSanitizer" not in r.stderr, r.stderr[-4000:]
     bad = subprocess.run([sys.executable, script, "--inject"], env=env, capture_output=True, text=True, timeout=300)
     assert bad.returncode != 0 and "heap-buffer-overflow" in bad.stderr and "sim_kernel" in bad.stderr

@@ -389,7 +389,7 @@ def main():
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": spec["desc"], "replications_per_gpu_per_step": n_total_rank,
                        "rng": "philox4x32-10", "log_ring_records_per_replication": log_cap,
-                       "slab_layout": os.environ.get("MSIM_SLAB_LAYOUT", "soa"),
+                       "slab_layout": os.environ.get("MSIM_SLAB_LAYOUT", "aos"),
                        "l2": "flushed with a 256 MB write between timed steps"},
             "replications_per_sec": reps_total / (total_ms * 1e-3),
             "events_per_replication": events / reps_total,

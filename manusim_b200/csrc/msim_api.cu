@@ -26,7 +26,7 @@ static int fail(int code, const std::string& msg) { g_err = msg; return code; }
 struct msim_handle_s {
     KParams kp;                 // layout + scalar parameters (args filled per run)
     int policy;
-    int aos;                    // 1: array-of-structures slab + msim::aos kernels (experimental, MSIM_SLAB_LAYOUT=aos)
+    int aos;                    // 1: array-of-structures slab + msim::aos kernels (default); 0: MSIM_SLAB_LAYOUT=soa
     int n_sms;
     int warps_per_block[2];     // per rng mode (the Philox and replay kernels differ in register use)
     int blocks_per_sm[2];
@@ -109,9 +109,15 @@ extern "C" int msim_create(const msim_tables_t* t, msim_handle_t* out) {
     memset(&h->kp, 0, sizeof(h->kp));
     h->policy = t->policy;
     {
-        const char* lay = getenv("MSIM_SLAB_LAYOUT");       // read per handle; default = the measured SoA kernel
-        h->aos = lay && strcmp(lay, "aos") == 0;
-        if (lay && !h->aos && strcmp(lay, "soa") != 0) { delete h; return fail(MSIM_E_INVALID, "MSIM_SLAB_LAYOUT must be soa or aos"); }
+        // Slab layout, read per handle.  Default: array-of-structures (msim_kernel_aos.cu), +6..7 % on a B200
+        // (profiles/r01_slab_layout_probe.jsonl); MSIM_SLAB_LAYOUT=soa selects the structure-of-arrays build
+        // (msim_kernel.cu) that all earlier round-1 measurements were taken with.
+        const char* lay = getenv("MSIM_SLAB_LAYOUT");
+        h->aos = !(lay && strcmp(lay, "soa") == 0);
+        if (lay && strcmp(lay, "soa") != 0 && strcmp(lay, "aos") != 0) {
+            delete h;
+            return fail(MSIM_E_INVALID, "MSIM_SLAB_LAYOUT must be soa or aos");
+        }
     }
     h->d_scratch = nullptr; h->scratch_bytes = 0;
     Lay& L = h->kp.lay;

@@ -1,19 +1,21 @@
-// msim_kernel_aos.cu -- EXPERIMENTAL twin of msim_kernel.cu with an array-of-structures replication slab.
+// msim_kernel_aos.cu -- the simulation kernel with an array-of-structures replication slab (the DEFAULT build).
 //
 // Same execution model, same handlers, same cooperative phases and synchronisation points as msim_kernel.cu (read
 // that file's header first); the only difference is where lane 0's entity state lives inside the warp's slab:
 //   * msim_kernel.cu   : one array per field (r_utf[R], r_tbf[R], ..., po_qty[MP], ...), each at its own byte
 //                        offset from the layout table -> every access is  LDCU offset; IADD3 idx+offset+slab; LDS;
 //   * this file        : one small struct per resource (28 B, at slab offset 0), product (24 B), production order
-//                        (12 / 16 B) and demand order (16 B) -> one IMAD per ENTITY, then LDS/STS with immediate
-//                        field offsets.  Handlers touch 3-8 fields of the same entity, so the address arithmetic
-//                        (about a third of the handler instructions in the SoA build) mostly disappears and the warm
-//                        code shrinks -- the kernel is instruction-fetch bound (profiles/README.md).
+//                        (12 / 16 B) and demand order (12 B + 2 link bytes) -> one IMAD per ENTITY, then LDS/STS with
+//                        immediate field offsets.  Handlers touch 3-8 fields of the same entity, so part of the address
+//                        arithmetic disappears and the code shrinks by 4-10 % (the kernel is instruction-fetch bound,
+//                        profiles/README.md).
 // Fields read by the WHOLE warp stay structure-of-arrays (calendar, per-order timers, event FIFOs, log staging,
 // variate buffer) and so do the rarely used DBR / queue-logging side arrays.
-// Selected per handle with MSIM_SLAB_LAYOUT=aos (msim_api.cu); the default stays the measured SoA kernel until
-// this one has been timed on a B200.  Bit-exactness is checked like the default kernel's (tests/test_emu_kernel.py
-// on CPU fibers, tests/test_gpu_parity.py with MSIM_SLAB_LAYOUT=aos on the GPU).
+// Measured on a B200 (profiles/r01_slab_layout_probe.jsonl): +7.2 % on the 20-resource job shop, +6.1 % on toc_dbr,
+// identical trajectories.  MSIM_SLAB_LAYOUT=soa (read by msim_create) selects msim_kernel.cu instead, the build every
+// earlier round-1 number and ncu capture was taken with; it stays until this one has the same depth of profiles.
+// Bit-exactness is checked like the other kernel's: tests/test_emu_kernel.py on CPU fibers (both layouts, goldens, fuzz,
+// ASan/UBSan) and the -m gpu tests (whatever layout the environment selects).
 #include <cuda_runtime.h>
 #include <math_constants.h>
 #include "msim_device.cuh"

@@ -1,7 +1,8 @@
 #!/usr/bin/env python
 """GPU: smoke() for both slab layouts, then one short timing of each on the bench workload (jobshop20, shortened).
-Not a bench line -- a first look at whether the experimental array-of-structures kernel is worth a full measurement.
-usage: python tools/layout_probe.py [run_until] [replications]"""
+Not a bench line -- a quick A/B of the two slab layouts (array-of-structures = default, structure-of-arrays =
+MSIM_SLAB_LAYOUT=soa) on identical trajectories.
+usage: python tools/layout_probe.py [run_until] [replications] [workload] [nosmoke]"""
 import json
 import os
 import sys
@@ -15,6 +16,8 @@ sys.path.insert(0, str(ROOT))
 def main():
     ru = int(sys.argv[1]) if len(sys.argv) > 1 else 1000
     n = int(sys.argv[2]) if len(sys.argv) > 2 else 5920
+    workload = sys.argv[3] if len(sys.argv) > 3 else "jobshop20"
+    smoke = not (len(sys.argv) > 4 and sys.argv[4] == "nosmoke")
     import torch
 
     import __graft_entry__ as g
@@ -25,12 +28,14 @@ def main():
     for layout in ("soa", "aos"):
         os.environ["MSIM_SLAB_LAYOUT"] = layout
         t0 = time.time()
-        g.smoke()
+        if smoke:
+            g.smoke()
         out[f"smoke_{layout}_s"] = round(time.time() - t0, 2)
-        spec = bench.workload_spec("jobshop20", ru)
-        (cfg, res, prod), policy, _, _ = spec["parts"][0]
-        mpo, mdo = spec["pools"][0]
-        eng = BatchEngine(compile_scenario(cfg, res, prod, policy=policy, max_production_orders=mpo, max_demand_orders=mdo))
+        spec = bench.workload_spec(workload, ru)
+        (cfg, res, prod), policy, _, _ = spec["parts"][-1]
+        mpo, mdo = spec["pools"][-1]
+        eng = BatchEngine(compile_scenario(cfg, res, prod, policy=policy, dbr_repair=spec.get("dbr_repair", False),
+                                           max_production_orders=mpo, max_demand_orders=mdo))
         r = eng.alloc(n, 0, 0)
         for rep in range(3):
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

@@ -5,8 +5,11 @@ from __future__ import annotations
 import ctypes as C
 from pathlib import Path
 
+import os
+
 PKG = Path(__file__).resolve().parent
-LIB_PATH = PKG / "libmsim.so"
+# MSIM_LIB: load another build of the same library (A/B variants made by manusim_b200.build.build_lib(tag=...))
+LIB_PATH = Path(os.environ["MSIM_LIB"]) if os.environ.get("MSIM_LIB") else PKG / "libmsim.so"
 
 EXPORTS = ["msim_version", "msim_last_error", "msim_create", "msim_destroy", "msim_query", "msim_run",
            "msim_run_host", "msim_reduce_metrics", "msim_reduce_variables", "msim_test_philox", "msim_test_variates"]

@@ -28,16 +28,23 @@ def needs_build() -> bool:
     return any(d.stat().st_mtime > t for d in deps)
 
 
-def build_lib(force: bool = False, verbose: bool = False) -> Path:
-    """One nvcc per translation unit (in parallel), then one link: libmsim.so holds the default kernel
-    (msim_kernel.cu), its experimental array-of-structures twin (msim_kernel_aos.cu) and the C ABI (msim_api.cu)."""
-    if not force and not needs_build():
+def variant_path(tag: str) -> Path:
+    """A/B builds (tools/ab_probe.py): same sources, extra -D switches, loaded with MSIM_LIB=<path>."""
+    return PKG / f"libmsim_{tag}.so"
+
+
+def build_lib(force: bool = False, verbose: bool = False, defines=(), tag: str = "") -> Path:
+    """One nvcc per translation unit (in parallel), then one link: libmsim.so holds the simulation kernel in its two
+    slab layouts (msim_kernel_aos.cu = default, msim_kernel.cu = MSIM_SLAB_LAYOUT=soa) and the C ABI (msim_api.cu).
+    `tag` + `defines` build an experiment variant next to it (libmsim_<tag>.so)."""
+    LIB = variant_path(tag) if tag else globals()["LIB"]
+    if not force and not tag and not needs_build():
         return LIB
     nvcc = _nvcc()
     flags = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC",
-             "-Xptxas", "-v" if verbose else "-O3"]
-    objdir = PKG / "build"
-    objdir.mkdir(exist_ok=True)
+             "-Xptxas", "-v" if verbose else "-O3"] + [f"-D{d}" for d in defines]
+    objdir = PKG / "build" / (tag or "default")
+    objdir.mkdir(parents=True, exist_ok=True)
     objs, procs = [], []
     for s in SOURCES:
         o = objdir / (Path(s).stem + ".o")

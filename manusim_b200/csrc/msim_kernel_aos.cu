@@ -27,6 +27,21 @@
 #define batch_many batch_many_aos
 #include "philox.cuh"
 
+// ---- experiment switches for A/B builds (tools/ab_probe.py); all 0 = the build that was measured.  Every variant
+// is checked bit for bit on the CPU-fiber emulation before it gets GPU time (`python tools/ab_probe.py verify`).
+// (Tried and dropped because nvcc emits byte-identical SASS: __builtin_expect on the error / option branches, and
+//  an equality chain on the four hottest micro-events in front of the handler switch -- it is folded back into it.)
+#ifndef MSIM_X_NTO         // 1: calendar pops are not counted one by one: n_timeouts = timers created - timers pending
+#define MSIM_X_NTO 0
+#endif
+#ifndef MSIM_X_TAILPUSH    // 1: the "successor is not alone -> push it and leave" exits of the chained handlers share
+#define MSIM_X_TAILPUSH 0  //    one out-of-line push at the end of the switch (shorter straight-line hot path)
+#endif
+#if MSIM_X_TAILPUSH
+#define PUSH_AND_LEAVE(ev) { tail_ev = (ev); goto L_TAIL_PUSH; }
+#else
+#define PUSH_AND_LEAVE(ev) { pushN(ev); break; }
+#endif
 namespace msim {
 namespace aos {
 
@@ -473,6 +488,9 @@ struct Sim {
         int a = (ev >> 8) & 0xFF;
         int b = (ev >> 16) & 0xFF;
         nev++;
+#if MSIM_X_TAILPUSH
+        uint32_t tail_ev;
+#endif
         switch (op) {
         case OP_TO_WARMUP:                                       // factory_sim.py:97-99
             warm = 1;
@@ -486,7 +504,7 @@ struct Sim {
             DORD(float, due, d) = __fadd_rn(PRD(float, ddue, a), now);
             DORD(float, arr, d) = now;
             list_append<kDoStride>(&sc->inb_head, &sc->inb_tail, DO_NEXT, d);
-            if (!alone()) { pushN(EV(OP_PUT_INBOUND, a, 0)); break; }
+            if (!alone()) PUSH_AND_LEAVE(EV(OP_PUT_INBOUND, a, 0))
             nev++;                                               // StorePut[inbound] popped right away
         }
         // fall through
@@ -529,7 +547,7 @@ struct Sim {
             if (DBR) ARR(uint8_t, po_relpy)[b] = (uint8_t)now_py;
             list_append<kPoStride>(&RES(uint8_t, inh, first), &RES(uint8_t, int, first), PO_NEXT, b);
             PORD(uint8_t, loc, b) = LOC_IN;
-            if (!alone()) { pushN(EV(OP_REL_PUT1, first, b)); break; }
+            if (!alone()) PUSH_AND_LEAVE(EV(OP_REL_PUT1, first, b))
             a = first;
             nev++;                                               // StorePut[input of the first resource] popped right away
         }
@@ -540,7 +558,7 @@ struct Sim {
             if (!(q > 0.0f)) { fail(MSIM_ST_AMOUNT_NONPOSITIVE); break; }
             int prod = PORD(uint8_t, prod, b);
             PRD(float, wip, prod) = __fadd_rn(PRD(float, wip, prod), q);
-            if (!alone()) { pushN(EV(OP_REL_PUT2, a, b)); break; }
+            if (!alone()) PUSH_AND_LEAVE(EV(OP_REL_PUT2, a, b))
             nev++;                                               // ContainerPut[wip] popped right away
         }
         // fall through
@@ -569,7 +587,7 @@ struct Sim {
             }
             RES(uint8_t, cur, a) = (uint8_t)b;
             PORD(uint8_t, loc, b) = LOC_PROC;
-            if (!(force || alone())) { pushN(EV(OP_MACH_PUTPROC, a, 0)); break; }
+            if (!(force || alone())) PUSH_AND_LEAVE(EV(OP_MACH_PUTPROC, a, 0))
             nev++;                                               // StorePut[processing] popped right away
         }
         // fall through
@@ -577,7 +595,7 @@ struct Sim {
             float setup = draw_scalar_hot(1, TAB(DDist, t_setup)[a]);
             RES(float, setup, a) = setup;
             if (warm) emit(ringR(RM_SETUP, a), now, setup);
-            if (!(force || alone())) { pushN(EV(OP_MACH_REQ, a, 0)); break; }
+            if (!(force || alone())) PUSH_AND_LEAVE(EV(OP_MACH_REQ, a, 0))
             nev++;                                               // Request popped right away
         }
         // fall through
@@ -590,7 +608,8 @@ struct Sim {
                 nev++;                                           // Timeout(0): lands on this timestamp and is popped right away
             }
             // fall through
-        case OP_TO_SETUP: {                                      // :425-440
+        case OP_TO_SETUP:
+        {                                      // :425-440
             uint32_t po = RES(uint8_t, cur, a);
             int prod = PORD(uint8_t, prod, po);
             int step = TAB(uint16_t, t_route_start)[prod] + PORD(uint8_t, done, po);
@@ -621,7 +640,8 @@ struct Sim {
             timer(a, __fadd_rn(now, __double2float_rn(total)), EV(OP_TO_PROC, a, 0));
             break;
         }
-        case OP_TO_PROC: {                                       // :442-451
+        case OP_TO_PROC:
+        {                                       // :442-451
             uint32_t po = RES(uint8_t, cur, a);
             float busy;
             if (DBR && now_py && (ARR(uint8_t, r_flags)[a] & F_START_PY)) {
@@ -643,7 +663,7 @@ struct Sim {
             RES(float, busy, a) = busy;
             PORD(uint8_t, done, po)++;
             PORD(uint8_t, loc, po) = LOC_NONE;
-            if (!alone()) { pushN(EV(OP_MACH_GOTPROC, a, 0)); break; }
+            if (!alone()) PUSH_AND_LEAVE(EV(OP_MACH_GOTPROC, a, 0))
             nev++;                                               // StoreGet[processing] popped right away
         }
         // fall through
@@ -651,7 +671,7 @@ struct Sim {
             uint32_t po = RES(uint8_t, cur, a);
             list_append<kPoStride>(&RES(uint8_t, outh, a), &RES(uint8_t, outt, a), PO_NEXT, po);
             PORD(uint8_t, loc, po) = LOC_OUT;
-            if (!alone()) { pushN(EV(OP_MACH_PUTOUT, a, 0)); break; }
+            if (!alone()) PUSH_AND_LEAVE(EV(OP_MACH_PUTOUT, a, 0))
             nev++;                                               // StorePut[output] popped right away
         }
         // fall through
@@ -695,7 +715,7 @@ struct Sim {
         case OP_TRANS_GOT:                                       // _transportation :300-304
             RES(uint8_t, tcur, a) = (uint8_t)b;
             PORD(uint8_t, loc, b) = LOC_TRANS;
-            if (!alone()) { pushN(EV(OP_TRANS_PUT, a, 0)); break; }
+            if (!alone()) PUSH_AND_LEAVE(EV(OP_TRANS_PUT, a, 0))
             nev++;                                               // StorePut[transport] popped right away
             // fall through
         case OP_TRANS_PUT: {                                     // :306-310 / :329-335
@@ -704,7 +724,7 @@ struct Sim {
             int total = TAB(uint16_t, t_route_start)[prod + 1] - TAB(uint16_t, t_route_start)[prod];
             PORD(uint8_t, loc, po) = LOC_NONE;
             const bool last = PORD(uint8_t, done, po) == total;
-            if (last || !alone()) { pushN(EV(last ? OP_TRANS_GOT2_FINAL : OP_TRANS_GOT2_NEXT, a, 0)); break; }
+            if (last || !alone()) PUSH_AND_LEAVE(EV(last ? OP_TRANS_GOT2_FINAL : OP_TRANS_GOT2_NEXT, a, 0))
             nev++;                                               // StoreGet[transport] popped right away
         }
         // fall through
@@ -714,7 +734,7 @@ struct Sim {
             int nxt = TAB(uint8_t, t_step_res)[TAB(uint16_t, t_route_start)[prod] + PORD(uint8_t, done, po)];
             list_append<kPoStride>(&RES(uint8_t, inh, nxt), &RES(uint8_t, int, nxt), PO_NEXT, po);
             PORD(uint8_t, loc, po) = LOC_IN;
-            if (!alone()) { pushN(EV(OP_TRANS_PUTIN, a, nxt)); break; }
+            if (!alone()) PUSH_AND_LEAVE(EV(OP_TRANS_PUTIN, a, nxt))
             b = nxt;
             nev++;                                               // StorePut[input of the next resource] popped right away
         }
@@ -733,7 +753,7 @@ struct Sim {
             uint32_t po = RES(uint8_t, tcur, a);
             int prod = PORD(uint8_t, prod, po);
             PRD(float, fg, prod) = __fadd_rn(PRD(float, fg, prod), PORD(float, qty, po));
-            if (!alone()) { pushN(EV(OP_TRANS_FGPUT, a, 0)); break; }
+            if (!alone()) PUSH_AND_LEAVE(EV(OP_TRANS_FGPUT, a, 0))
             nev++;                                               // ContainerPut[finished goods] popped right away
         }
         // fall through
@@ -745,7 +765,7 @@ struct Sim {
             float w = PRD(float, wip, prod);
             if (!(w >= q)) { fail(MSIM_ST_WIP_GET_BLOCKED); break; }
             PRD(float, wip, prod) = __fsub_rn(w, q);
-            if (!alone()) { pushN(EV(OP_TRANS_WIPGET, a, 0)); break; }
+            if (!alone()) PUSH_AND_LEAVE(EV(OP_TRANS_WIPGET, a, 0))
             nev++;                                               // ContainerGet[wip] popped right away
         }
         // fall through
@@ -866,6 +886,11 @@ struct Sim {
         default:
             break;
         }
+#if MSIM_X_TAILPUSH
+        return;
+    L_TAIL_PUSH:
+        pushN(tail_ev);
+#endif
     }
 
     // process_order continuation: constraint_buffer_level += ccr_add; env.process(_release_order(po))
@@ -1226,7 +1251,9 @@ __global__ void __launch_bounds__(256, 5) sim_kernel(const __grid_constant__ KPa
                     s.same_left = cnt - 1u;
                     if (cnt > 1u) s.attn |= A_SAME;
                 }
+#if !MSIM_X_NTO
                 sc->n_timeouts++;
+#endif
                 uint32_t ev;
                 if (DBR) s.now_py = 0;     // Environment._now takes the type of the popped entry (Appendix B.2)
                 if (slot < L.NT) {
@@ -1267,10 +1294,32 @@ __global__ void __launch_bounds__(256, 5) sim_kernel(const __grid_constant__ KPa
                 __syncwarp();
             }
         }
+#if MSIM_X_NTO
+        // calendar pops = timers created (tseq) - timers still pending: every pop consumed exactly one entry
+        uint32_t pend = 0;
+        {
+            const uint32_t inf = __float_as_uint(CUDART_INF_F);
+#pragma unroll 1
+            for (int i = lane; i < L.NT; i += 32) pend += reinterpret_cast<const uint32_t*>(sb + L.tm_time)[i] != inf;
+            if (on_due) {
+#pragma unroll 1
+                for (int i = lane; i < L.MD; i += 32) pend += reinterpret_cast<const uint32_t*>(sb + L.do_tt)[i] != inf;
+            }
+            if (DBR) {
+#pragma unroll 1
+                for (int i = lane; i < L.MP; i += 32) pend += reinterpret_cast<const uint32_t*>(sb + L.po_tt)[i] != inf;
+            }
+            pend = __reduce_add_sync(FULLMASK, pend);
+        }
+#endif
         if (lane == 0) {
             p.a.n_events[rep] = (unsigned long long)s.nev + 1ull;     // + the stop event of run(until)
             p.a.status[rep] = s.status;
+#if MSIM_X_NTO
+            if (p.a.n_timeouts) p.a.n_timeouts[rep] = s.tseq - pend;
+#else
             if (p.a.n_timeouts) p.a.n_timeouts[rep] = sc->n_timeouts;
+#endif
             if (p.a.log_count && rep < p.a.n_log_reps) p.a.log_count[rep] = s.logc;
             if (RNG == MSIM_RNG_PHILOX && p.a.rec_count) {
                 for (int k = 0; k < 4; ++k) p.a.rec_count[rep * 4 + k] = sc->draw[k];

@@ -36,12 +36,19 @@ FLAVOURS = {
 }
 
 
-def lib_path(flavour: str = "plain") -> Path:
-    return BUILD / ("libmsim_emu.so" if flavour == "plain" else f"libmsim_emu_{flavour}.so")
+def _tag(flavour, defines):
+    return flavour + "".join("_" + d.replace("=", "") for d in defines)
+
+
+def lib_path(flavour: str = "plain", defines=()) -> Path:
+    t = _tag(flavour, defines)
+    return BUILD / ("libmsim_emu.so" if t == "plain" else f"libmsim_emu_{t}.so")
 
 
 def build(flavour: str = "plain", force: bool = False, extra_defines=()) -> Path:
-    out = lib_path(flavour)
+    """extra_defines: the kernel's experiment switches (e.g. ("MSIM_X_COLD=1",)) -> a separately named library"""
+    extra_defines = tuple(extra_defines)
+    out = lib_path(flavour, extra_defines)
     if not force and out.exists() and all(d.stat().st_mtime <= out.stat().st_mtime for d in DEPS):
         return out
     BUILD.mkdir(exist_ok=True)
@@ -50,7 +57,7 @@ def build(flavour: str = "plain", force: bool = False, extra_defines=()) -> Path
            + [f"-D{d}" for d in extra_defines])
     objs, procs = [], []
     for s in SOURCES:                     # one g++ per translation unit, in parallel
-        o = BUILD / f"{s.stem}_{flavour}.o"
+        o = BUILD / f"{s.stem}_{_tag(flavour, extra_defines)}.o"
         objs.append(str(o))
         procs.append(subprocess.Popen(cmd + ["-c", "-x", "c++", str(s), "-o", str(o)], stdout=subprocess.PIPE,
                                       stderr=subprocess.PIPE, text=True))
@@ -66,12 +73,13 @@ def build(flavour: str = "plain", force: bool = False, extra_defines=()) -> Path
 _libs = {}
 
 
-def load(flavour: str = "plain"):
-    if flavour in _libs:
-        return _libs[flavour]
+def load(flavour: str = "plain", defines=()):
+    key = _tag(flavour, tuple(defines))
+    if key in _libs:
+        return _libs[key]
     from manusim_b200 import _lib as L
 
-    lib = C.CDLL(str(build(flavour)))
+    lib = C.CDLL(str(build(flavour, extra_defines=defines)))
     lib.msim_version.restype = C.c_int
     lib.msim_last_error.restype = C.c_char_p
     lib.msim_create.argtypes = [C.POINTER(L.Tables), C.POINTER(C.c_void_p)]
@@ -80,19 +88,19 @@ def load(flavour: str = "plain"):
     lib.msim_run.argtypes = [C.c_void_p, C.POINTER(L.RunArgs)]
     lib.msim_reduce_metrics.argtypes = [C.c_void_p] * 4 + [C.c_int64, C.c_void_p, C.c_void_p]
     lib.msim_reduce_variables.argtypes = [C.c_void_p] * 4 + [C.c_int64, C.c_void_p, C.c_void_p]
-    _libs[flavour] = lib
+    _libs[key] = lib
     return lib
 
 
 class EmuEngine:
     """numpy twin of manusim_b200.engine.BatchEngine.run for the emulated library ("device" memory = host memory)."""
 
-    def __init__(self, tables, flavour: str = "plain", layout: str | None = None):
+    def __init__(self, tables, flavour: str = "plain", layout: str | None = None, defines=()):
         from manusim_b200 import _lib as L
         from manusim_b200.engine import make_ctables
 
         self.L = L
-        self.lib = load(flavour)
+        self.lib = load(flavour, defines)
         self.tables = tables
         ct, self._keep = make_ctables(tables)
         self.handle = C.c_void_p()

@@ -250,6 +250,7 @@ def main():
 
     total = 0.0
     warm = 0                    # static instructions executed more than once per 1000 SimPy events
+    warm_by_func = defaultdict(int)
     by_func = defaultdict(float)
     by_line = defaultdict(float)
     by_op = defaultdict(float)
@@ -274,6 +275,7 @@ def main():
         total += ex
         if ex / info["events"] > 1e-3:
             warm += 1
+            warm_by_func[func_name(*next(((f, l) for f, l in chain if f in lines), chain[-1]))] += 1
         inner = next(((f, l) for f, l in chain if f in lines), chain[-1])      # innermost line of OUR sources
         by_line[inner] += ex
         by_func[func_name(inner[0], inner[1])] += ex
@@ -290,6 +292,9 @@ def main():
     print("\nby function (innermost source function of each instruction)")
     for fn, v in sorted(by_func.items(), key=lambda kv: -kv[1])[:20]:
         print(f"  {v / ev:7.3f}  {fn}")
+    print("\nwarm static instructions by function (x16 B)")
+    for fn, v in sorted(warm_by_func.items(), key=lambda kv: -kv[1])[:25]:
+        print(f"  {v:6d}  {fn}")
     print("\nby opcode")
     for op, v in sorted(by_op.items(), key=lambda kv: -kv[1])[:15]:
         print(f"  {v / ev:7.3f}  {op}")

@@ -352,7 +352,8 @@ def main():
                 "kernel_ms_per_launch": kern_ms / max(n_launch, 1), "launches": n_launch,
                 "algorithmic_bytes_per_launch": alg_bytes / max(n_launch, 1),
                 "note": "path is instruction-fetch / issue bound, not HBM bound (SURVEY 8(d)): 86 warp instructions per "
-                        "SimPy event, issue slots 40 % busy, stall_no_instruction dominant (profiles/README.md)",
+                        "SimPy event, issue slots 40 % busy, stall_no_instruction dominant (ncu capture of the SoA "
+                        "slab build, profiles/README.md; the AoS slab that is now the default was A/B-timed only)",
                 "kernel_share_of_step": kern_ms / sum(step_ms)}
 
     # ---- end to end through the public host-buffer API: pinned H2D of the step's inputs + D2H of its results

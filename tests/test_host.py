@@ -129,3 +129,33 @@ def test_ctypes_mirror_matches_the_c_header(tmp_path):
         assert int(out[cname]) == ctypes.sizeof(cls), cname
         for fname, *_ in cls._fields_:
             assert int(out[f"{cname}.{fname}"]) == getattr(cls, fname).offset, (cname, fname)
+
+
+def test_library_refuses_without_device_and_validates_the_layout_switch(monkeypatch):
+    """msim_create through the real libmsim.so on a box without a GPU: a bad MSIM_SLAB_LAYOUT is an argument error,
+    a good one gets as far as the device query and fails there -- there is no host execution path in the library."""
+    import torch
+
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    from manusim_b200 import _lib
+    from manusim_b200.engine import make_ctables
+
+    lib = _lib.load()
+    cfg, res, prod = scenarios.toy2()
+    ct, keep = make_ctables(compile_scenario(cfg, res, prod))
+    h = ctypes.c_void_p()
+    monkeypatch.setenv("MSIM_SLAB_LAYOUT", "bogus")
+    assert lib.msim_create(ctypes.byref(ct), ctypes.byref(h)) == -1
+    assert b"MSIM_SLAB_LAYOUT" in lib.msim_last_error()
+    for layout in ("aos", "soa"):
+        monkeypatch.setenv("MSIM_SLAB_LAYOUT", layout)
+        assert lib.msim_create(ctypes.byref(ct), ctypes.byref(h)) == -2          # MSIM_E_CUDA
+        assert b"no CPU fallback" in lib.msim_last_error()
+
+
+def test_product_never_loads_the_emulated_library():
+    """tests/emu is test infrastructure: nothing under manusim_b200/, bench.py or __graft_entry__.py refers to it."""
+    for f in list((ROOT / "manusim_b200").rglob("*.py")) + [ROOT / "bench.py", ROOT / "__graft_entry__.py"]:
+        txt = f.read_text()
+        assert "tests/emu" not in txt and "libmsim_emu" not in txt and "import emu" not in txt, f

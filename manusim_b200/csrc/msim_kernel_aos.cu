@@ -37,6 +37,21 @@
 #ifndef MSIM_X_TAILPUSH    // 1: the "successor is not alone -> push it and leave" exits of the chained handlers share
 #define MSIM_X_TAILPUSH 0  //    one out-of-line push at the end of the switch (shorter straight-line hot path)
 #endif
+// upper bound of what compile-time (template) option flags would buy: the flag is a constant of the variant build,
+// which is then only valid for workloads that use that value (jobshop20 / toc_dbr benches: no queue records, no tape
+// recording)
+#ifdef MSIM_X_FIXED_LOGQ
+#define LOGQ (MSIM_X_FIXED_LOGQ)
+#else
+#define LOGQ (p.log_queues)
+#endif
+#ifdef MSIM_X_FIXED_REC
+#define RECORDING (MSIM_X_FIXED_REC)
+#define NOT_RECORDING (!(MSIM_X_FIXED_REC))
+#else
+#define RECORDING (p.a.rec_cap > 0)
+#define NOT_RECORDING (p.a.rec_cap == 0)
+#endif
 #if MSIM_X_TAILPUSH
 #define PUSH_AND_LEAVE(ev) { tail_ev = (ev); goto L_TAIL_PUSH; }
 #else
@@ -152,7 +167,7 @@ __device__ __noinline__ double philox_draw_slow(const KParams& p, Scal* sc, cons
         }
         out = (double)v;
     }
-    if (p.a.rec_cap > 0 && (long long)idx < p.a.rec_cap) {
+    if (RECORDING && (long long)idx < p.a.rec_cap) {
         if (stream == 2) p.a.rec_C[rep * p.a.rec_cap + idx] = out;
         else (stream == 0 ? p.a.rec_A : (stream == 1 ? p.a.rec_B : p.a.rec_D))[rep * p.a.rec_cap + idx] = (float)out;
     }
@@ -224,7 +239,7 @@ struct Sim {
         const uint32_t idx = sc->draw[stream];
         const uint32_t off = idx - sc->rb_base[stream];
         if (off >= (uint32_t)kXuBuf - kXuRefillAt) rb_need |= 1u << stream;
-        if (off >= (uint32_t)kXuBuf || p.a.rec_cap > 0) return false;
+        if (off >= (uint32_t)kXuBuf || RECORDING) return false;
         const float2 xu = ARR(float2, rb)[(stream - 1) * kXuBuf + off];
         if (d.kind == MSIM_DIST_NORMAL) {
             v = d.d0 + d.d1 * xu.x;
@@ -251,7 +266,7 @@ struct Sim {
             if (idx >= sc->tlen[stream]) { fail(MSIM_ST_TAPE_EXHAUSTED); return 0.0f; }
             return __ldg(reinterpret_cast<const float*>(sc->tbase[stream]) + idx);
         }
-        if (d.kind == MSIM_DIST_CONSTANT && p.a.rec_cap == 0) {   // max(0, np.float32(params[0])): no generator involved
+        if (d.kind == MSIM_DIST_CONSTANT && NOT_RECORDING) {   // max(0, np.float32(params[0])): no generator involved
             sc->draw[stream]++;
             return d.d0 > 0.0f ? d.d0 : 0.0f;
         }
@@ -566,18 +581,18 @@ struct Sim {
             float q = PORD(float, qty, b);
             int prod = PORD(uint8_t, prod, b);
             sc->tot_wip = __fadd_rn(sc->tot_wip, q);
-            if (p.log_queues) ARR(float, r_qq)[a] = __fadd_rn(ARR(float, r_qq)[a], q);
+            if (LOGQ) ARR(float, r_qq)[a] = __fadd_rn(ARR(float, r_qq)[a], q);
             if (warm) {
                 emit(ringP(PM_RELEASED, prod), now, q);
                 inventory(prod, true, false);
-                if (p.log_queues) queue_log_add(a, q);
+                if (LOGQ) queue_log_add(a, q);
             }
             nev++;                                               // process-end event
             break;
         }
         case OP_MACH_GOT:                                        // _production_system :380-395
         L_MACH_GOT: {
-            if (p.log_queues) {
+            if (LOGQ) {
                 float q = PORD(float, qty, b);
                 ARR(float, r_qq)[a] = __fsub_rn(ARR(float, r_qq)[a], q);
                 if (warm) {
@@ -681,7 +696,7 @@ struct Sim {
             // / draws / calendar entries in the same relative order whether interleaved event by event (SimPy) or run
             // one after the other, so the machine chain may run right here.  Not for DBR (its dispatch scans observe
             // order locations) nor with queue logging (both chains write `queue` records).
-            const bool solo = !DBR && !p.log_queues && alone();
+            const bool solo = !DBR && !LOGQ && alone();
             if (((sc->trans_wait >> a) & 1u) && RES(uint8_t, outh, a) != kNone) {
                 uint32_t po = list_pop<kPoStride>(&RES(uint8_t, outh, a), &RES(uint8_t, outt, a), PO_NEXT);
                 PORD(uint8_t, loc, po) = LOC_NONE;
@@ -741,7 +756,7 @@ struct Sim {
         // fall through
         case OP_TRANS_PUTIN: {                                   // :336-358
             serve_mach(b);
-            if (p.log_queues) {
+            if (LOGQ) {
                 float q = PORD(float, qty, RES(uint8_t, tcur, a));
                 ARR(float, r_qq)[b] = __fadd_rn(ARR(float, r_qq)[b], q);
                 if (warm) queue_log_add(b, q);
@@ -1100,7 +1115,7 @@ __global__ void __launch_bounds__(256, 5) sim_kernel(const __grid_constant__ KPa
         #pragma unroll 1
         for (int i = lane; i < L.R; i += 32) {
             RES(uint8_t, inh, i) = kNone; RES(uint8_t, int, i) = kNone; RES(uint8_t, outh, i) = kNone; RES(uint8_t, outt, i) = kNone;
-            if (p.log_queues) reinterpret_cast<float*>(sb + L.r_lastq)[i] = CUDART_NAN_F;
+            if (LOGQ) reinterpret_cast<float*>(sb + L.r_lastq)[i] = CUDART_NAN_F;
         }
         #pragma unroll 1
         for (int i = lane; i < L.P; i += 32) {
@@ -1382,6 +1397,10 @@ int launch_sim(const KParams& p, int policy, int rng_mode, int grid, int block, 
 #undef DORD
 #undef PO_NEXT
 #undef DO_NEXT
+#undef LOGQ
+#undef RECORDING
+#undef NOT_RECORDING
+#undef PUSH_AND_LEAVE
 
 } // namespace aos
 } // namespace msim

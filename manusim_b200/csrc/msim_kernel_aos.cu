@@ -34,6 +34,9 @@
 #ifndef MSIM_X_NTO         // 1: calendar pops are not counted one by one: n_timeouts = timers created - timers pending
 #define MSIM_X_NTO 0
 #endif
+#ifndef MSIM_X_FLUSHGRP    // 1: the log flush sums each ring group by walking ITS members (max group size iterations)
+#define MSIM_X_FLUSHGRP 0  //    instead of broadcasting all n staged records to every lane (n iterations); same sums
+#endif
 #ifndef MSIM_X_TAILPUSH    // 1: the "successor is not alone -> push it and leave" exits of the chained handlers share
 #define MSIM_X_TAILPUSH 0  //    one out-of-line push at the end of the switch (shorter straight-line hot path)
 #endif
@@ -1064,10 +1067,23 @@ __device__ __forceinline__ void warp_flush(const KParams& p, const unsigned char
     bool leader = ((uint32_t)lane < n) && (lane == __ffs(grp) - 1);
     double tot = 0.0;
     float v = __uint_as_float(rec.y);
+#if MSIM_X_FLUSHGRP
+    {
+        unsigned m = (uint32_t)lane < n ? grp : 0u;                  // members of my ring's group still to add
+        const unsigned iters = __reduce_max_sync(FULLMASK, (unsigned)__popc(m));
+        for (unsigned it = 0; it < iters; ++it) {                    // ascending lanes = emission order, as below
+            const int j = m ? __ffs(m) - 1 : lane;
+            float vj = __shfl_sync(FULLMASK, v, j);
+            if (m) tot += (double)vj;
+            m &= m - 1u;
+        }
+    }
+#else
     for (uint32_t j = 0; j < n; ++j) {
         float vj = __shfl_sync(FULLMASK, v, (int)j);
         if ((grp >> j) & 1u) tot += (double)vj;
     }
+#endif
     if (leader) {
         p.a.acc_sum[rep * L.K + rec.z] += tot;
         p.a.acc_cnt[rep * L.K + rec.z] += (uint32_t)__popc(grp);

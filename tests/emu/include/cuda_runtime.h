@@ -62,7 +62,7 @@ emu_dim3 bdim();
 unsigned char* dyn_smem();
 // every participating lane contributes `v`; returns a pointer to the 32 contributions of the warp (valid until the
 // caller's next collective).  `kind` names the primitive: lanes meeting at different primitives is an error.
-enum Kind { K_SYNCWARP = 1, K_SHFL, K_SHFL_XOR, K_BALLOT, K_MATCH, K_REDUX_MIN, K_REDUX_ADD };
+enum Kind { K_SYNCWARP = 1, K_SHFL, K_SHFL_XOR, K_BALLOT, K_MATCH, K_REDUX_MIN, K_REDUX_ADD, K_REDUX_MAX };
 const uint64_t* warp_gather(unsigned mask, uint64_t v, int kind);
 void block_barrier();
 // run `body` once per thread of a grid x block launch (blocks spread over host threads)
@@ -124,6 +124,13 @@ static inline unsigned __reduce_min_sync(unsigned mask, unsigned v) {
     unsigned r = 0xFFFFFFFFu;
     for (int i = 0; i < 32; ++i)
         if ((mask >> i) & 1u) r = std::min(r, (unsigned)all[i]);
+    return r;
+}
+static inline unsigned __reduce_max_sync(unsigned mask, unsigned v) {
+    const uint64_t* all = emu::warp_gather(mask, v, emu::K_REDUX_MAX);
+    unsigned r = 0;
+    for (int i = 0; i < 32; ++i)
+        if ((mask >> i) & 1u) r = std::max(r, (unsigned)all[i]);
     return r;
 }
 static inline unsigned __reduce_add_sync(unsigned mask, unsigned v) {

@@ -27,7 +27,8 @@ sys.path.insert(0, str(ROOT))
 VARIANTS = {
     "nto": ["MSIM_X_NTO=1"],
     "tailpush": ["MSIM_X_TAILPUSH=1"],
-    "nto_tailpush": ["MSIM_X_NTO=1", "MSIM_X_TAILPUSH=1"],
+    "flushgrp": ["MSIM_X_FLUSHGRP=1"],
+    "nto_tailpush_flushgrp": ["MSIM_X_NTO=1", "MSIM_X_TAILPUSH=1", "MSIM_X_FLUSHGRP=1"],
     # option flags as build constants: NOT a general build (ignores log_queues / tape recording), only an upper bound
     # of what templating those flags would buy on the bench workloads
     "fixedopts": ["MSIM_X_FIXED_LOGQ=0", "MSIM_X_FIXED_REC=0"],

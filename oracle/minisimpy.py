@@ -12,6 +12,10 @@ installable here (no network, no wheel in /opt/wheelhouse).  This module
 restates SimPy's published algorithm from its documentation / source as
 remembered; it has never been diffed against the
 real package.  The reference ships no tests or golden vectors for this layer.
+The only external anchor available offline: the example programs and printed
+outputs of SimPy's documentation, restated from memory in
+``tests/test_minisimpy_documented_behaviour.py`` (tie-breaking, Resource and
+Store hand-over order, ``run(until)``).
 
 Semantics restated (SimPy 4.1.1 module in brackets):
   * [core.Environment] heap of ``(time, priority, eid, event)``; URGENT=0,

@@ -144,3 +144,59 @@ def test_run_until_semantics():
         assert "must be > the current simulation time" in str(e)
     else:
         raise AssertionError("until <= now must raise")
+
+
+def test_filter_store_machine_shop_example():
+    """Topical guide on stores: FilterStore.get(filter) -- the reference's resource_input queues are FilterStores
+    (src/manusim/engine/stores.py:37-41) and simple_scheduler picks orders through an identity filter."""
+    from collections import namedtuple
+
+    out = []
+    Machine = namedtuple("Machine", "size, duration")
+    m1 = Machine(1, 2)
+    m2 = Machine(2, 1)
+    env = simpy.Environment()
+    machine_shop = simpy.FilterStore(env, capacity=2)
+    machine_shop.items = [m1, m2]
+
+    def user(name, env, ms, size):
+        machine = yield ms.get(lambda machine: machine.size == size)
+        out.append(f"{name} got {machine} at {env.now}")
+        yield env.timeout(machine.duration)
+        yield ms.put(machine)
+        out.append(f"{name} released {machine} at {env.now}")
+
+    [env.process(user(i, env, machine_shop, (i % 2) + 1)) for i in range(3)]
+    env.run()
+    assert out == ["0 got Machine(size=1, duration=2) at 0", "1 got Machine(size=2, duration=1) at 0",
+                   "1 released Machine(size=2, duration=1) at 1", "0 released Machine(size=1, duration=2) at 2",
+                   "2 got Machine(size=1, duration=2) at 2", "2 released Machine(size=1, duration=2) at 4"]
+
+
+def test_container_rules():
+    """resources/container.py: amount <= 0 raises at construction of the request; a get larger than the level blocks
+    and blocks the getters behind it (head-of-line), a put wakes them in order."""
+    env = simpy.Environment()
+    c = simpy.Container(env, init=1)
+    for bad in (0, -1):
+        try:
+            c.put(bad)
+        except ValueError as e:
+            assert "must be > 0" in str(e)
+        else:
+            raise AssertionError
+    got = []
+
+    def getter(name, amount):
+        yield c.get(amount)
+        got.append((name, env.now, c.level))
+
+    def putter():
+        yield env.timeout(1)
+        yield c.put(2)
+
+    env.process(getter("big", 3))        # cannot be served from level 1
+    env.process(getter("small", 1))      # could be, but waits behind "big"
+    env.process(putter())
+    env.run()
+    assert got == [("big", 1, 0)] and c.level == 0 and len(c.get_queue) == 1

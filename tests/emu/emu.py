@@ -86,6 +86,7 @@ def load(flavour: str = "plain", defines=()):
     lib.msim_destroy.argtypes = [C.c_void_p]
     lib.msim_query.argtypes = [C.c_void_p, C.POINTER(L.Info)]
     lib.msim_run.argtypes = [C.c_void_p, C.POINTER(L.RunArgs)]
+    lib.msim_run_host.argtypes = [C.c_void_p, C.POINTER(L.HostArgs)]
     lib.msim_reduce_metrics.argtypes = [C.c_void_p] * 4 + [C.c_int64, C.c_void_p, C.c_void_p]
     lib.msim_reduce_variables.argtypes = [C.c_void_p] * 4 + [C.c_int64, C.c_void_p, C.c_void_p]
     _libs[key] = lib
@@ -180,6 +181,48 @@ class EmuEngine:
             a.log, a.log_count = out.log.ctypes.data, out.log_count.ctypes.data
             a.log_cap, a.n_log_reps = log_cap, out.log.shape[0]
         self._check(self.lib.msim_run(self.handle, C.byref(a)))
+        out._keep = keep
+        return out
+
+    def run_host(self, n_reps, seed=0, rep_offset=0, tapes=None, rep_seeds=None, n_log_reps=0, log_cap=0):
+        """msim_run_host (host-buffer twin of msim_run: scratch carving, H2D staging, D2H copy-back in msim_api.cu)."""
+        from manusim_b200.engine import pack_tapes
+
+        K = self.K
+        out = SimpleNamespace(
+            acc_sum=np.full((n_reps, K), np.nan), acc_cnt=np.full((n_reps, K), 0x7FFFFFFF, dtype=np.uint32),
+            n_events=np.zeros(n_reps, dtype=np.uint64), n_timeouts=np.zeros(n_reps, dtype=np.uint32),
+            status=np.full(n_reps, 8, dtype=np.int32), log=None, log_count=None)
+        a = self.L.HostArgs()
+        a.n_reps, a.rep_offset, a.philox_seed = n_reps, rep_offset, seed & 0xFFFFFFFFFFFFFFFF
+        keep = []
+        if tapes is not None:
+            a.rng_mode = 1
+            packed = tapes if isinstance(tapes, dict) else pack_tapes(tapes)
+            for k in "ABCD":
+                v = np.array(packed[k], copy=True)
+                o = np.array(packed[k + "_off"], dtype=np.int64, copy=True)
+                if int(o[-1]) < len(v):
+                    v = v[: max(int(o[-1]), 0)].copy() if int(o[-1]) > 0 else np.zeros(0, dtype=v.dtype)
+                keep += [v, o]
+                setattr(a, "tape_" + k, v.ctypes.data if len(v) else 0)
+                setattr(a, f"tape_{k}_off", o.ctypes.data)
+        else:
+            a.rng_mode = 0
+            if rep_seeds is not None:
+                rs = np.ascontiguousarray(rep_seeds, dtype=np.uint64)
+                keep.append(rs)
+                a.rep_seeds = rs.ctypes.data
+        a.acc_sum, a.acc_cnt = out.acc_sum.ctypes.data, out.acc_cnt.ctypes.data
+        a.n_events, a.n_timeouts, a.status = out.n_events.ctypes.data, out.n_timeouts.ctypes.data, out.status.ctypes.data
+        if n_log_reps > 0 and log_cap > 0:
+            out.log = np.zeros((min(n_log_reps, n_reps), log_cap, 4), dtype=np.int32)
+            out.log_count = np.zeros(min(n_log_reps, n_reps), dtype=np.uint32)
+            a.log, a.log_count = out.log.ctypes.data, out.log_count.ctypes.data
+            a.log_cap, a.n_log_reps = log_cap, out.log.shape[0]
+        ms = C.c_double(-1.0)
+        a.kernel_ms = C.pointer(ms)
+        self._check(self.lib.msim_run_host(self.handle, C.byref(a)))
         out._keep = keep
         return out
 

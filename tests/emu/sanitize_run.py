@@ -37,6 +37,11 @@ def replay(name, n=2):
         np.array_equal(val, g["value"]), name
     eng.reduce(res)
     eng.reduce(res, variables=True)
+    # host-buffer entry point: scratch carving + staging + copy-back (msim_api.cu) under the sanitizers
+    h = eng.run_host(n + 1, tapes=[{k: g["tape_" + k] for k in "ABCD"}] * (n + 1), n_log_reps=n, log_cap=len(g["ring"]) + 8)
+    assert np.array_equal(h.n_events[:n], res.n_events) and np.array_equal(h.log_count, res.log_count), name
+    h = eng.run_host(3, seed=5)
+    assert h.status.shape == (3,)
     eng.close()
 
 

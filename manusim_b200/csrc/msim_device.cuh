@@ -49,6 +49,12 @@ struct Scal {
     uint8_t drain_wait;     // _update_constraint_buffer blocked on resource_finished[CCR].get()
     uint8_t fin_n;          // items in resource_finished[CCR]
     uint8_t fin[5];
+#if defined(MSIM_X_DUECACHE) && MSIM_X_DUECACHE
+    // experiment (msim_kernel_aos.cu): earliest pending onDue delivery timer, kept up to date by lane 0 so that the
+    // per-pop scan of all demand-order timers only runs after one of them fired
+    uint32_t due_t, due_e, due_slot, due_cnt;   // float bits of the earliest time, its smallest eid, calendar slot, ties
+    uint32_t due_dirty;
+#endif
 };
 
 // byte offsets of every per-replication array inside the warp's shared-memory slab and of every table

@@ -37,6 +37,9 @@
 #ifndef MSIM_X_FLUSHGRP    // 1: the log flush sums each ring group by walking ITS members (max group size iterations)
 #define MSIM_X_FLUSHGRP 0  //    instead of broadcasting all n staged records to every lane (n iterations); same sums
 #endif
+#ifndef MSIM_X_DUECACHE    // 1: onDue delivery timers: lane 0 keeps the earliest one cached; the MD-entry scan of every calendar
+#define MSIM_X_DUECACHE 0  //    pop runs only after a delivery timer fired (about one pop in eight)
+#endif
 #ifndef MSIM_X_TAILPUSH    // 1: the "successor is not alone -> push it and leave" exits of the chained handlers share
 #define MSIM_X_TAILPUSH 0  //    one out-of-line push at the end of the switch (shorter straight-line hot path)
 #endif
@@ -831,6 +834,13 @@ struct Sim {
                         pushN(EV(OP_TO_SHIP, a, b));
                     } else {
                         ARR(float, do_tt)[b] = t;
+#if MSIM_X_DUECACHE
+                        if (!sc->due_dirty) {            // a new timer has the largest eid so far: it only wins on time
+                            const uint32_t tb = __float_as_uint(t);
+                            if (tb < sc->due_t) { sc->due_t = tb; sc->due_e = tseq; sc->due_slot = (uint32_t)(p.lay.NT + b); sc->due_cnt = 1u; }
+                            else if (tb == sc->due_t) sc->due_cnt++;
+                        }
+#endif
                         ARR(uint32_t, do_eid)[b] = tseq++;
                     }
                     break;
@@ -1144,6 +1154,10 @@ __global__ void __launch_bounds__(256, 5) sim_kernel(const __grid_constant__ KPa
         }
         if (lane == 0) {
             sc->inb_head = kNone; sc->inb_tail = kNone; sc->po_free = 0; sc->do_free = 0;
+#if MSIM_X_DUECACHE
+            sc->due_t = __float_as_uint(CUDART_INF_F); sc->due_e = 0xFFFFFFFFu; sc->due_slot = 0u; sc->due_cnt = 0u;
+            sc->due_dirty = 0u;
+#endif
             sc->rb_base[0] = sc->rb_base[1] = sc->rb_base[2] = 0u - (uint32_t)kXuBuf;   // empty: index 0 is 16 past the base
             if (RNG == MSIM_RNG_REPLAY) {
                 long long oa = p.a.tape_A_off[rep], ob = p.a.tape_B_off[rep], oc = p.a.tape_C_off[rep], od = p.a.tape_D_off[rep];
@@ -1226,6 +1240,40 @@ __global__ void __launch_bounds__(256, 5) sim_kernel(const __grid_constant__ KPa
                         else if (t == bt) { leq++; if (e < be) { be = e; bslot = i; } }
                     }
                 }
+#if MSIM_X_DUECACHE
+                if (on_due) {
+                    if (__shfl_sync(FULLMASK, lane == 0 ? sc->due_dirty : 0u, 0)) {
+                        // a delivery timer fired since the last scan: recompute (earliest time, smallest eid at that
+                        // time, its slot, number of timers tied on that time) over the demand-order timers
+                        const uint32_t* dt = reinterpret_cast<const uint32_t*>(sb + L.do_tt);
+                        const uint32_t* de = reinterpret_cast<const uint32_t*>(sb + L.do_eid);
+                        uint32_t dbt = 0xFFFFFFFFu, dbe = 0xFFFFFFFFu, dleq = 0u;
+                        int dslot = -1;
+#pragma unroll 1
+                        for (int i = lane; i < L.MD; i += 32) {
+                            const uint32_t t = dt[i], e = de[i];
+                            if (t < dbt) { dbt = t; dbe = e; dslot = L.NT + i; dleq = 1u; }
+                            else if (t == dbt) { dleq++; if (e < dbe) { dbe = e; dslot = L.NT + i; } }
+                        }
+                        const uint32_t dmin = __reduce_min_sync(FULLMASK, dbt);
+                        const bool dmine = dbt == dmin;
+                        const uint32_t demin = __reduce_min_sync(FULLMASK, dmine ? dbe : 0xFFFFFFFFu);
+                        const uint32_t dcnt = __reduce_add_sync(FULLMASK, dmine ? dleq : 0u);
+                        const unsigned dwho = __ballot_sync(FULLMASK, dmine && dbe == demin);
+                        const int ds = __shfl_sync(FULLMASK, dslot, __ffs(dwho) - 1);
+                        if (lane == 0) {
+                            sc->due_t = dmin; sc->due_e = demin; sc->due_slot = (uint32_t)ds; sc->due_cnt = dcnt;
+                            sc->due_dirty = 0u;
+                        }
+                        __syncwarp();
+                    }
+                    if (lane == 0) {                      // the cached timer is one more candidate of lane 0
+                        const uint32_t t = sc->due_t, e = sc->due_e;
+                        if (t < bt) { bt = t; be = e; bslot = (int)sc->due_slot; leq = (int)sc->due_cnt; }
+                        else if (t == bt) { leq += (int)sc->due_cnt; if (e < be) { be = e; bslot = (int)sc->due_slot; } }
+                    }
+                }
+#else
                 if (on_due) {
                     const uint32_t* dt = reinterpret_cast<const uint32_t*>(sb + L.do_tt);
                     const uint32_t* de = reinterpret_cast<const uint32_t*>(sb + L.do_eid);
@@ -1236,6 +1284,7 @@ __global__ void __launch_bounds__(256, 5) sim_kernel(const __grid_constant__ KPa
                         else if (t == bt) { leq++; if (e < be) { be = e; bslot = L.NT + i; } }
                     }
                 }
+#endif
                 if (DBR) {
                     const uint32_t* pt = reinterpret_cast<const uint32_t*>(sb + L.po_tt);
                     const uint32_t* pe = reinterpret_cast<const uint32_t*>(sb + L.po_eid);
@@ -1306,6 +1355,9 @@ __global__ void __launch_bounds__(256, 5) sim_kernel(const __grid_constant__ KPa
                     int d = slot - L.NT;
                     ev = EV(OP_TO_SHIP, DORD(uint8_t, prod, d), d);
                     reinterpret_cast<float*>(sb + L.do_tt)[d] = CUDART_INF_F;
+#if MSIM_X_DUECACHE
+                    sc->due_dirty = 1u;
+#endif
                 } else {
                     int po = slot - L.NT - L.MD;
                     ev = EV(OP_TO_DORDER, 0, po);

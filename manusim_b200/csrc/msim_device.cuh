@@ -55,6 +55,9 @@ struct Scal {
     uint32_t due_t, due_e, due_slot, due_cnt;   // float bits of the earliest time, its smallest eid, calendar slot, ties
     uint32_t due_dirty;
 #endif
+#if defined(MSIM_X_ROPECACHE) && MSIM_X_ROPECACHE
+    uint32_t rope_t, rope_e, rope_slot, rope_cnt, rope_dirty;   // same for the DBR process_order delay timers
+#endif
 };
 
 // byte offsets of every per-replication array inside the warp's shared-memory slab and of every table

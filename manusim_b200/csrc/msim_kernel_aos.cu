@@ -40,6 +40,9 @@
 #ifndef MSIM_X_DUECACHE    // 1: onDue delivery timers: lane 0 keeps the earliest one cached; the MD-entry scan of every calendar
 #define MSIM_X_DUECACHE 0  //    pop runs only after a delivery timer fired (about one pop in eight)
 #endif
+#ifndef MSIM_X_ROPECACHE   // 1: the same cache for the DBR process_order delay timers (scan of MP entries per pop)
+#define MSIM_X_ROPECACHE 0
+#endif
 #ifndef MSIM_X_TAILPUSH    // 1: the "successor is not alone -> push it and leave" exits of the chained handlers share
 #define MSIM_X_TAILPUSH 0  //    one out-of-line push at the end of the switch (shorter straight-line hot path)
 #endif
@@ -871,6 +874,14 @@ struct Sim {
                         pushN(EV(OP_TO_DORDER, 0, b));
                     } else {
                         ARR(float, po_tt)[b] = t;
+#if MSIM_X_ROPECACHE
+                        if (!sc->rope_dirty) {
+                            const uint32_t tb = __float_as_uint(t);
+                            const uint32_t slot_ = (uint32_t)(p.lay.NT + p.lay.MD + b);
+                            if (tb < sc->rope_t) { sc->rope_t = tb; sc->rope_e = tseq; sc->rope_slot = slot_; sc->rope_cnt = 1u; }
+                            else if (tb == sc->rope_t) sc->rope_cnt++;
+                        }
+#endif
                         ARR(uint32_t, po_eid)[b] = tseq++;
                     }
                 } else {
@@ -1154,6 +1165,10 @@ __global__ void __launch_bounds__(256, 5) sim_kernel(const __grid_constant__ KPa
         }
         if (lane == 0) {
             sc->inb_head = kNone; sc->inb_tail = kNone; sc->po_free = 0; sc->do_free = 0;
+#if MSIM_X_ROPECACHE
+            sc->rope_t = __float_as_uint(CUDART_INF_F); sc->rope_e = 0xFFFFFFFFu; sc->rope_slot = 0u; sc->rope_cnt = 0u;
+            sc->rope_dirty = 0u;
+#endif
 #if MSIM_X_DUECACHE
             sc->due_t = __float_as_uint(CUDART_INF_F); sc->due_e = 0xFFFFFFFFu; sc->due_slot = 0u; sc->due_cnt = 0u;
             sc->due_dirty = 0u;
@@ -1285,6 +1300,38 @@ __global__ void __launch_bounds__(256, 5) sim_kernel(const __grid_constant__ KPa
                     }
                 }
 #endif
+#if MSIM_X_ROPECACHE
+                if (DBR) {
+                    if (__shfl_sync(FULLMASK, lane == 0 ? sc->rope_dirty : 0u, 0)) {
+                        const uint32_t* pt = reinterpret_cast<const uint32_t*>(sb + L.po_tt);
+                        const uint32_t* pe = reinterpret_cast<const uint32_t*>(sb + L.po_eid);
+                        uint32_t dbt = 0xFFFFFFFFu, dbe = 0xFFFFFFFFu, dleq = 0u;
+                        int dslot = -1;
+#pragma unroll 1
+                        for (int i = lane; i < L.MP; i += 32) {
+                            const uint32_t t = pt[i], e = pe[i];
+                            if (t < dbt) { dbt = t; dbe = e; dslot = L.NT + L.MD + i; dleq = 1u; }
+                            else if (t == dbt) { dleq++; if (e < dbe) { dbe = e; dslot = L.NT + L.MD + i; } }
+                        }
+                        const uint32_t dmin = __reduce_min_sync(FULLMASK, dbt);
+                        const bool dmine = dbt == dmin;
+                        const uint32_t demin = __reduce_min_sync(FULLMASK, dmine ? dbe : 0xFFFFFFFFu);
+                        const uint32_t dcnt = __reduce_add_sync(FULLMASK, dmine ? dleq : 0u);
+                        const unsigned dwho = __ballot_sync(FULLMASK, dmine && dbe == demin);
+                        const int ds = __shfl_sync(FULLMASK, dslot, __ffs(dwho) - 1);
+                        if (lane == 0) {
+                            sc->rope_t = dmin; sc->rope_e = demin; sc->rope_slot = (uint32_t)ds; sc->rope_cnt = dcnt;
+                            sc->rope_dirty = 0u;
+                        }
+                        __syncwarp();
+                    }
+                    if (lane == 0) {
+                        const uint32_t t = sc->rope_t, e = sc->rope_e;
+                        if (t < bt) { bt = t; be = e; bslot = (int)sc->rope_slot; leq = (int)sc->rope_cnt; }
+                        else if (t == bt) { leq += (int)sc->rope_cnt; if (e < be) { be = e; bslot = (int)sc->rope_slot; } }
+                    }
+                }
+#else
                 if (DBR) {
                     const uint32_t* pt = reinterpret_cast<const uint32_t*>(sb + L.po_tt);
                     const uint32_t* pe = reinterpret_cast<const uint32_t*>(sb + L.po_eid);
@@ -1295,6 +1342,7 @@ __global__ void __launch_bounds__(256, 5) sim_kernel(const __grid_constant__ KPa
                         else if (t == bt) { leq++; if (e < be) { be = e; bslot = L.NT + L.MD + i; } }
                     }
                 }
+#endif
             }
             if (RNG == MSIM_RNG_PHILOX) {
                 // ---- opportunistic bulk refill of the precomputed (x,u) pairs: the warp is converged here anyway
@@ -1362,6 +1410,9 @@ __global__ void __launch_bounds__(256, 5) sim_kernel(const __grid_constant__ KPa
                     int po = slot - L.NT - L.MD;
                     ev = EV(OP_TO_DORDER, 0, po);
                     reinterpret_cast<float*>(sb + L.po_tt)[po] = CUDART_INF_F;
+#if MSIM_X_ROPECACHE
+                    sc->rope_dirty = 1u;
+#endif
                 }
                 first_ev = ev;
             }

@@ -29,6 +29,7 @@ VARIANTS = {
     "tailpush": ["MSIM_X_TAILPUSH=1"],
     "flushgrp": ["MSIM_X_FLUSHGRP=1"],
     "duecache": ["MSIM_X_DUECACHE=1"],
+    "ropecache": ["MSIM_X_ROPECACHE=1"],
     "nto_tailpush_flushgrp": ["MSIM_X_NTO=1", "MSIM_X_TAILPUSH=1", "MSIM_X_FLUSHGRP=1"],
     # option flags as build constants: NOT a general build (ignores log_queues / tape recording), only an upper bound
     # of what templating those flags would buy on the bench workloads

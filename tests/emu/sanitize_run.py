@@ -67,9 +67,9 @@ def philox(policy, mode, repair=False, log_queues=False):
 def main():
     inject = "--inject" in sys.argv
     cases = 0
-    # (CTA shape, slab layout): the default kernel with the product's CTA shape and with one warp per CTA, then the
-    # experimental array-of-structures twin with one warp per CTA
-    for wpb, layout in () if inject else (("", "soa"), ("1", "soa"), ("1", "aos")):
+    # (CTA shape, slab layout): the default (array-of-structures) kernel with the product's CTA shape and with one warp
+    # per CTA, then the structure-of-arrays build with one warp per CTA
+    for wpb, layout in () if inject else (("", "aos"), ("1", "aos"), ("1", "soa")):
         os.environ["MSIM_SLAB_LAYOUT"] = layout
         if wpb:
             os.environ["MSIM_EMU_WPB"] = wpb

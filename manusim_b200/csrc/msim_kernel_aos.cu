@@ -18,6 +18,7 @@
 // ASan/UBSan) and the -m gpu tests (whatever layout the environment selects).
 #include <cuda_runtime.h>
 #include <math_constants.h>
+#include <stdlib.h>
 #include "msim_device.cuh"
 // philox.cuh defines four out-of-line device functions in namespace msim; nvcc also emits (empty) host definitions for
 // them, which would collide with msim_kernel.cu's at link time -> this translation unit gets its own names
@@ -46,21 +47,13 @@
 #ifndef MSIM_X_TAILPUSH    // 1: the "successor is not alone -> push it and leave" exits of the chained handlers share
 #define MSIM_X_TAILPUSH 0  //    one out-of-line push at the end of the switch (shorter straight-line hot path)
 #endif
-// upper bound of what compile-time (template) option flags would buy: the flag is a constant of the variant build,
-// which is then only valid for workloads that use that value (jobshop20 / toc_dbr benches: no queue records, no tape
-// recording)
-#ifdef MSIM_X_FIXED_LOGQ
-#define LOGQ (MSIM_X_FIXED_LOGQ)
-#else
-#define LOGQ (p.log_queues)
-#endif
-#ifdef MSIM_X_FIXED_REC
-#define RECORDING (MSIM_X_FIXED_REC)
-#define NOT_RECORDING (!(MSIM_X_FIXED_REC))
-#else
-#define RECORDING (p.a.rec_cap > 0)
-#define NOT_RECORDING (p.a.rec_cap == 0)
-#endif
+// Option flags as a template parameter: OPTS bit 0 = the scenario may log `queue` records (config log_queues), bit 1 =
+// the run may record variate tapes (rec_cap > 0).  OPTS = 3 is the general kernel; OPTS = 0 ("lean") drops both
+// branches from every handler (-8 % code) and is launched instead when neither option is in use and MSIM_LEAN=1
+// (off by default until it has been timed on a B200; tools/ab_probe.py times it as variant "lean").
+#define LOGQ (((OPTS) & 1) && p.log_queues)
+#define RECORDING (((OPTS) & 2) && p.a.rec_cap > 0)
+#define NOT_RECORDING (!((OPTS) & 2) || p.a.rec_cap == 0)
 #if MSIM_X_TAILPUSH
 #define PUSH_AND_LEAVE(ev) { tail_ev = (ev); goto L_TAIL_PUSH; }
 #else
@@ -150,6 +143,7 @@ __device__ __forceinline__ double pyround6(double x) { return __ddiv_rn(rint(__d
 // demand triplets) and as the fallback of the inlined fast paths (buffer miss, Marsaglia-Tsang squeeze failure,
 // shape < 1, batches of more than one sample, tape recording).  Bumps the stream's draw index itself.
 // count < 0: scalar draw (DistributionGenerator.random_number, clamped at 0); count >= 0: batch sum.
+template <int OPTS>
 __device__ __noinline__ double philox_draw_slow(const KParams& p, Scal* sc, const float2* rb, long long rep, int stream,
                                                 const DDist* d, int count) {
     const uint32_t idx = sc->draw[stream]++;
@@ -183,7 +177,7 @@ __device__ __noinline__ double philox_draw_slow(const KParams& p, Scal* sc, cons
     return out;
 }
 
-template <int POLICY, int RNG>
+template <int POLICY, int RNG, int OPTS>
 struct Sim {
     const KParams& p;
     unsigned char* sb;        // this warp's slab
@@ -267,7 +261,7 @@ struct Sim {
         if (RNG == MSIM_RNG_REPLAY) return draw_scalar(stream, d);
         float v;
         if (fast_sample(stream, d, v)) return v > 0.0f ? v : 0.0f;
-        return (float)philox_draw_slow(p, sc, ARR(float2, rb), rep, stream, &d, -1);
+        return (float)philox_draw_slow<OPTS>(p, sc, ARR(float2, rb), rep, stream, &d, -1);
     }
     __device__ __forceinline__ float draw_scalar(int stream, const DDist& d) {
         if (RNG == MSIM_RNG_REPLAY) {
@@ -279,7 +273,7 @@ struct Sim {
             sc->draw[stream]++;
             return d.d0 > 0.0f ? d.d0 : 0.0f;
         }
-        return (float)philox_draw_slow(p, sc, ARR(float2, rb), rep, stream, &d, -1);
+        return (float)philox_draw_slow<OPTS>(p, sc, ARR(float2, rb), rep, stream, &d, -1);
     }
     __device__ __forceinline__ double draw_batch(const DDist& d, int count) {
         if (RNG == MSIM_RNG_REPLAY) {
@@ -289,7 +283,7 @@ struct Sim {
         }
         float v;
         if (count == 1 && fast_sample(2, d, v)) return (double)((d.kind == MSIM_DIST_NORMAL && !(v > 0.0f)) ? 0.0f : v);
-        return philox_draw_slow(p, sc, ARR(float2, rb), rep, 2, &d, count < 0 ? 0 : count);
+        return philox_draw_slow<OPTS>(p, sc, ARR(float2, rb), rep, 2, &d, count < 0 ? 0 : count);
     }
 
     // ------------------------------------------------------------------ records (Logger.log, logs.py:44-66)
@@ -1112,7 +1106,7 @@ __device__ __forceinline__ void warp_flush(const KParams& p, const unsigned char
 }
 
 // ---------------------------------------------------------------------------------------------------------
-template <int POLICY, int RNG>
+template <int POLICY, int RNG, int OPTS>
 __global__ void __launch_bounds__(256, 5) sim_kernel(const __grid_constant__ KParams p) {
     MSIM_DYN_SMEM(smem);
     const Lay& L = p.lay;
@@ -1120,7 +1114,7 @@ __global__ void __launch_bounds__(256, 5) sim_kernel(const __grid_constant__ KPa
     const int warp = threadIdx.x >> 5;
     unsigned char* sb = smem + (size_t)warp * L.slab_bytes;
     Scal* sc = reinterpret_cast<Scal*>(sb + L.scal);
-    Sim<POLICY, RNG> s(p, sb, sc);
+    Sim<POLICY, RNG, OPTS> s(p, sb, sc);
     const bool on_due = p.delivery_mode == MSIM_DELIVERY_ON_DUE;
     constexpr bool DBR = POLICY == MSIM_POLICY_DBR;
     constexpr int kPoStride = aos_po_stride(POLICY), kDoStride = kAosDoLinkStride;
@@ -1465,23 +1459,32 @@ __global__ void __launch_bounds__(256, 5) sim_kernel(const __grid_constant__ KPa
 
 // ---------------------------------------------------------------------------------------------------------
 typedef void (*sim_fn)(const KParams);
-static sim_fn pick(int policy, int rng) {
-    if (policy == MSIM_POLICY_FIFO) return rng == MSIM_RNG_REPLAY ? sim_kernel<MSIM_POLICY_FIFO, MSIM_RNG_REPLAY>
-                                                                  : sim_kernel<MSIM_POLICY_FIFO, MSIM_RNG_PHILOX>;
+template <int OPTS>
+static sim_fn pick_opts(int policy, int rng) {
+    if (policy == MSIM_POLICY_FIFO) return rng == MSIM_RNG_REPLAY ? sim_kernel<MSIM_POLICY_FIFO, MSIM_RNG_REPLAY, OPTS>
+                                                                  : sim_kernel<MSIM_POLICY_FIFO, MSIM_RNG_PHILOX, OPTS>;
     if (policy == MSIM_POLICY_MAX_PRIORITY)
-        return rng == MSIM_RNG_REPLAY ? sim_kernel<MSIM_POLICY_MAX_PRIORITY, MSIM_RNG_REPLAY>
-                                      : sim_kernel<MSIM_POLICY_MAX_PRIORITY, MSIM_RNG_PHILOX>;
+        return rng == MSIM_RNG_REPLAY ? sim_kernel<MSIM_POLICY_MAX_PRIORITY, MSIM_RNG_REPLAY, OPTS>
+                                      : sim_kernel<MSIM_POLICY_MAX_PRIORITY, MSIM_RNG_PHILOX, OPTS>;
     if (policy == MSIM_POLICY_DBR)
-        return rng == MSIM_RNG_REPLAY ? sim_kernel<MSIM_POLICY_DBR, MSIM_RNG_REPLAY>
-                                      : sim_kernel<MSIM_POLICY_DBR, MSIM_RNG_PHILOX>;
+        return rng == MSIM_RNG_REPLAY ? sim_kernel<MSIM_POLICY_DBR, MSIM_RNG_REPLAY, OPTS>
+                                      : sim_kernel<MSIM_POLICY_DBR, MSIM_RNG_PHILOX, OPTS>;
     if (policy == MSIM_POLICY_EDD)
-        return rng == MSIM_RNG_REPLAY ? sim_kernel<MSIM_POLICY_EDD, MSIM_RNG_REPLAY>
-                                      : sim_kernel<MSIM_POLICY_EDD, MSIM_RNG_PHILOX>;
+        return rng == MSIM_RNG_REPLAY ? sim_kernel<MSIM_POLICY_EDD, MSIM_RNG_REPLAY, OPTS>
+                                      : sim_kernel<MSIM_POLICY_EDD, MSIM_RNG_PHILOX, OPTS>;
     return nullptr;
+}
+static sim_fn pick(int policy, int rng, bool lean) { return lean ? pick_opts<0>(policy, rng) : pick_opts<3>(policy, rng); }
+
+// MSIM_LEAN=1: runs that use neither queue records nor tape recording launch the OPTS = 0 kernels
+static bool lean_enabled() {              // (read per launch: a getenv costs nothing next to a kernel launch)
+    const char* e = getenv("MSIM_LEAN");
+    return e && e[0] == '1';
 }
 
 int sim_kernel_attrs(int policy, int rng_mode, size_t smem, int* regs, int block, int* blocks_per_sm) {
-    sim_fn f = pick(policy, rng_mode);
+    // (both option sets are compiled under the same launch bounds; the general kernel's occupancy is used for both)
+    sim_fn f = pick(policy, rng_mode, false);
     if (!f) return MSIM_E_UNSUPPORTED;
     cudaFuncAttributes at;
     if (cudaFuncGetAttributes(&at, f) != cudaSuccess) return MSIM_E_CUDA;
@@ -1496,13 +1499,14 @@ int sim_kernel_attrs(int policy, int rng_mode, size_t smem, int* regs, int block
 }
 
 int launch_sim(const KParams& p, int policy, int rng_mode, int grid, int block, size_t smem, void* stream) {
-    sim_fn f = pick(policy, rng_mode);
+    const bool lean = lean_enabled() && !p.log_queues && p.a.rec_cap == 0;
+    sim_fn f = pick(policy, rng_mode, lean);
     if (!f) return MSIM_E_UNSUPPORTED;
     // the opt-in limit is per function, not per handle: several handles with different slab sizes share a kernel
-    static size_t smem_set[4][2] = {{0, 0}, {0, 0}, {0, 0}, {0, 0}};
-    if (smem > smem_set[policy][rng_mode]) {
+    static size_t smem_set[2][4][2] = {};
+    if (smem > smem_set[lean][policy][rng_mode]) {
         if (cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return MSIM_E_CUDA;
-        smem_set[policy][rng_mode] = smem;
+        smem_set[lean][policy][rng_mode] = smem;
     }
     MSIM_LAUNCH(f, grid, block, smem, (cudaStream_t)stream, p);
     return cudaGetLastError() == cudaSuccess ? 0 : MSIM_E_CUDA;

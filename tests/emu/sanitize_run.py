@@ -69,8 +69,9 @@ def main():
     cases = 0
     # (CTA shape, slab layout): the default (array-of-structures) kernel with the product's CTA shape and with one warp
     # per CTA, then the structure-of-arrays build with one warp per CTA
-    for wpb, layout in () if inject else (("", "aos"), ("1", "aos"), ("1", "soa")):
+    for wpb, layout, lean in () if inject else (("", "aos", ""), ("1", "aos", "1"), ("1", "soa", "")):
         os.environ["MSIM_SLAB_LAYOUT"] = layout
+        os.environ["MSIM_LEAN"] = lean           # "1": runs without queue records / recording take the OPTS = 0 kernels
         if wpb:
             os.environ["MSIM_EMU_WPB"] = wpb
         else:
@@ -85,6 +86,7 @@ def main():
         philox("dbr", "instantly", repair=False)
         cases += 2
     os.environ.pop("MSIM_SLAB_LAYOUT", None)
+    os.environ.pop("MSIM_LEAN", None)
     if inject:
         g = load_golden("toy2")
         scn = g["scenario"]

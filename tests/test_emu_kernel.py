@@ -29,10 +29,25 @@ POLICY = {"base": "fifo", "simple_scheduler": "max_priority", "dbr": "dbr"}
 FULL = bool(os.environ.get("MSIM_EMU_FULL"))
 
 
+_asan_build = {}
+
+
 @pytest.fixture(scope="module")
 def emu():
+    import threading
+
     import emu as m
 
+    # the sanitizer flavour compiles while the plain-flavour tests run (different output files)
+    def _bg():
+        try:
+            _asan_build["path"] = m.build("asan")
+        except Exception as exc:            # re-raised by the sanitizer test
+            _asan_build["error"] = exc
+
+    t = threading.Thread(target=_bg, daemon=True)
+    t.start()
+    _asan_build["thread"] = t
     m.build("plain")
     return m
 
@@ -147,6 +162,34 @@ def test_host_buffer_entry_point_equals_device_buffer_entry_point(emu, name):
     assert np.array_equal(c.n_events, d.n_events) and np.array_equal(c.acc_sum, d.acc_sum)
 
 
+@pytest.mark.parametrize("name", ["toy2_instantly", "ss_lots", "ss_queues", "js20_ondue", "dbr_limits"])
+def test_lean_kernels_equal_the_general_ones(emu, name, monkeypatch):
+    """MSIM_LEAN=1 launches the OPTS = 0 instantiations (no queue-record / tape-recording branches) whenever a run uses
+    neither option; ss_queues (log_queues) and the recording run below must still take the general kernel."""
+    from manusim_b200.engine import decode_log
+
+    g = load_golden(name)
+    eng = _engine(emu, g["scenario"], "aos")
+    tapes = [{k: g["tape_" + k] for k in "ABCD"}] * 2
+    cap = len(g["ring"]) + 16
+    ref = eng.run(2, tapes=tapes, n_log_reps=2, log_cap=cap)
+    ref_p = eng.run(3, seed=21)
+    monkeypatch.setenv("MSIM_LEAN", "1")
+    r = eng.run(2, tapes=tapes, n_log_reps=2, log_cap=cap)
+    assert (r.status == 0).all() and (r.n_events == g["steps"]).all()
+    ring, tm, val, _ = decode_log(r.log[1], int(r.log_count[1]))
+    assert np.array_equal(ring, g["ring"].astype(np.uint32)) and np.array_equal(tm, g["time"]) and \
+        np.array_equal(val, g["value"])
+    for f in ("acc_sum", "acc_cnt", "n_events", "n_timeouts"):
+        assert np.array_equal(getattr(r, f), getattr(ref, f)), f
+    lean_p = eng.run(3, seed=21)                              # Philox, lean
+    rec_p = eng.run(3, seed=21, record_tapes=1 << 14)         # recording => general kernel
+    for f in ("acc_sum", "acc_cnt", "n_events", "n_timeouts", "status"):
+        assert np.array_equal(getattr(lean_p, f), getattr(ref_p, f)), f
+        assert np.array_equal(getattr(rec_p, f), getattr(ref_p, f)), f
+    assert rec_p.rec["count"].sum() > 0
+
+
 def test_emulated_reduction_kernels_match_numpy(emu):
     """msim_reduce_metrics / msim_reduce_variables (block-level shuffles + __syncthreads) against plain numpy."""
     g = load_golden("ss_lots")
@@ -181,6 +224,10 @@ def test_emulated_reduction_kernels_match_numpy(emu):
 def test_kernel_source_is_clean_under_address_and_ub_sanitizers(emu):
     """All eight simulation-kernel instantiations and both reductions under ASan + UBSan, product CTA shape and one
     warp per CTA; then the negative control (an output buffer one element short must abort the child)."""
+    if "thread" in _asan_build:
+        _asan_build["thread"].join()
+    if "error" in _asan_build:
+        raise _asan_build["error"]
     emu.build("asan")
     env = emu.asan_env()
     script = str(HERE / "emu" / "sanitize_run.py")

@@ -31,11 +31,11 @@ VARIANTS = {
     "duecache": ["MSIM_X_DUECACHE=1"],
     "ropecache": ["MSIM_X_ROPECACHE=1"],
     "nto_tailpush_flushgrp": ["MSIM_X_NTO=1", "MSIM_X_TAILPUSH=1", "MSIM_X_FLUSHGRP=1"],
-    # option flags as build constants: NOT a general build (ignores log_queues / tape recording), only an upper bound
-    # of what templating those flags would buy on the bench workloads
-    "fixedopts": ["MSIM_X_FIXED_LOGQ=0", "MSIM_X_FIXED_REC=0"],
 }
-RESTRICTED = {"fixedopts"}     # `verify` replays only goldens without queue records and skips the recording fuzz
+RESTRICTED = set()
+# variants of the DEFAULT library selected by environment (no rebuild): the other slab layout, and the "lean" kernels
+# without the queue-record / tape-recording branches (template parameter OPTS = 0, launched when MSIM_LEAN=1)
+ENV_VARIANTS = {"soa": {"MSIM_SLAB_LAYOUT": "soa"}, "lean": {"MSIM_LEAN": "1"}}
 
 WORKER = r"""
 import json, os, sys
@@ -159,7 +159,7 @@ def cmd_verify(_):
 def cmd_run(a):
     from manusim_b200.build import variant_path
 
-    tags = [("default", {}), ("soa", {"MSIM_SLAB_LAYOUT": "soa"})]
+    tags = [("default", {})] + list(ENV_VARIANTS.items())
     for tag in VARIANTS:
         if variant_path(tag).exists():
             tags.append((tag, {"MSIM_LIB": str(variant_path(tag))}))

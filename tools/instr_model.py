@@ -103,7 +103,8 @@ def sass_chains(layout, policy, rng=0):
                    capture_output=True)
     cubin = tmp / (Path(SRC[layout]).stem + ".sm_100a.cubin")
     txt = subprocess.run(["nvdisasm", "-gi", "-c", str(cubin)], capture_output=True, text=True, check=True).stdout
-    want = f"sim_kernelILi{POLICY_ID[policy]}ELi{rng}E"
+    # mangled kernel name: the AoS kernels carry a third template argument (OPTS; 3 = the general kernel)
+    want = f"sim_kernelILi{POLICY_ID[policy]}ELi{rng}E" + ("Li3EEEv" if layout == "aos" else "EEv")
     out = []                      # (opcode, chain) ; chain = [(file, line)] innermost first
     active = False
     pending = []

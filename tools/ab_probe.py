@@ -31,6 +31,7 @@ VARIANTS = {
     "duecache": ["MSIM_X_DUECACHE=1"],
     "ropecache": ["MSIM_X_ROPECACHE=1"],
     "nto_tailpush_flushgrp": ["MSIM_X_NTO=1", "MSIM_X_TAILPUSH=1", "MSIM_X_FLUSHGRP=1"],
+    "allx": ["MSIM_X_NTO=1", "MSIM_X_TAILPUSH=1", "MSIM_X_FLUSHGRP=1", "MSIM_X_DUECACHE=1", "MSIM_X_ROPECACHE=1"],
 }
 RESTRICTED = set()
 # variants of the DEFAULT library selected by environment (no rebuild): the other slab layout, and the "lean" kernels

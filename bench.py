@@ -244,6 +244,7 @@ def main():
         p["host"] = p["eng"].alloc_host(p["n"])
         p["seeds_host"] = torch.empty((p["n"],), dtype=torch.int64).pin_memory()
         p["seeds_dev"] = torch.empty((p["n"],), dtype=torch.int64, device=dev)
+        p["ev_part"] = torch.zeros((), dtype=torch.int64, device=dev)      # events of this part over the timed steps
     stats = torch.zeros((K, 3), dtype=torch.float64, device=dev)
     ev_total = torch.zeros((), dtype=torch.int64, device=dev)
     fail_total = torch.zeros((), dtype=torch.int64, device=dev)
@@ -289,6 +290,7 @@ def main():
         if timed:
             for p in parts:
                 ev_total.add_(p["res"].n_events.sum())
+                p["ev_part"].add_(p["res"].n_events.sum())
                 rec_total.add_(p["res"].acc_cnt.sum(dtype=torch.int64))
                 fail_total.add_((p["res"].status != 0).sum())
                 fail_codes.add_(torch.bincount(p["res"].status, minlength=9)[:9])
@@ -348,13 +350,31 @@ def main():
                 "traffic": (traffic_per_alg_byte * alg_bytes / max(n_launch, 1)) if traffic_per_alg_byte else None,
                 "traffic_source": "ncu dram__bytes_read.sum+dram__bytes_write.sum of one --set full capture, scaled by "
                                   "algorithmic bytes (profiles/r01_ncu_full_final.csv)",
-                "peak_source": peak_src, "kernel": "msim::sim_kernel<policy,rng>",
+                "peak_source": peak_src,
+                "kernel": ("msim::sim_kernel<policy,rng>" if os.environ.get("MSIM_SLAB_LAYOUT") == "soa"
+                           else "msim::aos::sim_kernel<policy,rng,opts>"),
                 "kernel_ms_per_launch": kern_ms / max(n_launch, 1), "launches": n_launch,
                 "algorithmic_bytes_per_launch": alg_bytes / max(n_launch, 1),
                 "note": "path is instruction-fetch / issue bound, not HBM bound (SURVEY 8(d)): 86 warp instructions per "
                         "SimPy event, issue slots 40 % busy, stall_no_instruction dominant (ncu capture of the SoA "
                         "slab build, profiles/README.md; the AoS slab that is now the default was A/B-timed only)",
                 "kernel_share_of_step": kern_ms / sum(step_ms)}
+
+    # per workload part (e.g. the asReady and the onDue half of jobshop20): simulation-kernel time and events/s of this
+    # rank over the timed steps -- reporting only, never allowed to break the line
+    try:
+        by_part = []
+        for i, p in enumerate(parts):
+            ms = sum(e0.elapsed_time(e1) for e0, e1, q in sim_events if q is p)
+            evp = int(p["ev_part"].item())
+            by_part.append({"part": i, "delivery_mode": spec["parts"][i][0][0].get("delivery_mode"),
+                            "replications_per_launch": p["n"], "kernel_ms_total": ms,
+                            "events_per_s": evp / (ms * 1e-3) if ms > 0 else None,
+                            "warps_per_sm": p["eng"].info["warps_per_block"] * p["eng"].info["blocks_per_sm"],
+                            "smem_per_replication": p["eng"].info["smem_per_replication"]})
+        roofline["kernel_by_part"] = by_part
+    except Exception as exc:                                   # pragma: no cover
+        roofline["kernel_by_part"] = f"unavailable: {exc!r}"
 
     # ---- end to end through the public host-buffer API: pinned H2D of the step's inputs + D2H of its results
     def e2e_step(step):

@@ -94,6 +94,29 @@ def scenario_table():
     simq.pop("print_mode", None)
     simq.update(run_until=300, warmup=40, memory_size=100000, log_queues=True)
     out["ss_queues"] = dict(cfg=simq, resources=resq, products=prodq, policy="base", seed=806309, patches=[])
+    # --- combinations no shipped config exercises (added late in round 1)
+    # max-priority dispatch x onDue delivery (patch P1): per-order delivery timers next to the priority scan
+    simo, reso, prodo, _ = _example("simple_scheduler")
+    simo.pop("print_mode", None)
+    simo.update(run_until=450, warmup=60, memory_size=100000, delivery_mode="onDue")
+    out["ss_ondue"] = dict(cfg=simo, resources=reso, products=prodo, policy="simple_scheduler", seed=427023,
+                           patches=["P1"])
+    # 20-resource job shop: lots > 1 (batch sums), queue records, frequent breakdowns, `instantly` delivery
+    cfg, res20c, prod20c = sc.jobshop20(run_until=700, warmup=100, mode="instantly")
+    cfg["log_queues"] = True
+    for i, r in enumerate(res20c.values()):
+        r["tbf"] = {"dist": "expo", "params": [90 + 11 * i]}
+        r["ttr"] = {"dist": "gamma", "params": [4, 3]}
+    for j, p_ in enumerate(prod20c.values()):
+        p_["demand"]["quantity"] = {"dist": "uniform", "params": [2, 0.5]}
+        p_["demand"]["freq"] = {"dist": "erlang", "params": [24 + j, 12]}
+    out["js20_lots_queues"] = dict(cfg=cfg, resources=res20c, products=prod20c, policy="base", seed=777001, patches=[])
+    # drum-buffer-rope x onDue delivery (P1 + P2 + P3): rope delay timers and delivery timers in one calendar
+    simd, resd, prodd, _ = _example("toc_dbr")
+    simd.pop("print_mode", None)
+    simd.update(run_until=1501, warmup=300, memory_size=200000, delivery_mode="onDue")
+    out["dbr_ondue"] = dict(cfg=simd, resources=resd, products=prodd, policy="dbr", seed=280679,
+                            patches=["P1", "P2", "P3"])
     # SimPy ValueError cases: negative batch delay, Container.put(0)
     cfg, res, prod = sc.toy2(run_until=400)
     prod["p1"]["processes"]["s1"]["processing_time"] = {"dist": "uniform", "params": [0.2, 2.0]}   # a < 0

@@ -44,6 +44,9 @@
 #ifndef MSIM_X_ROPECACHE   // 1: the same cache for the DBR process_order delay timers (scan of MP entries per pop)
 #define MSIM_X_ROPECACHE 0
 #endif
+#ifndef MSIM_X_MINBLOCKS   // __launch_bounds__(256, N): 5 = 51 registers (spills in the Philox kernels), 4 = 64 registers, no
+#define MSIM_X_MINBLOCKS 5 //    spills; free for handles that shared memory limits to 4 CTAs per SM anyway (onDue pools)
+#endif
 #ifndef MSIM_X_TAILPUSH    // 1: the "successor is not alone -> push it and leave" exits of the chained handlers share
 #define MSIM_X_TAILPUSH 0  //    one out-of-line push at the end of the switch (shorter straight-line hot path)
 #endif
@@ -1107,7 +1110,7 @@ __device__ __forceinline__ void warp_flush(const KParams& p, const unsigned char
 
 // ---------------------------------------------------------------------------------------------------------
 template <int POLICY, int RNG, int OPTS>
-__global__ void __launch_bounds__(256, 5) sim_kernel(const __grid_constant__ KParams p) {
+__global__ void __launch_bounds__(256, MSIM_X_MINBLOCKS) sim_kernel(const __grid_constant__ KParams p) {
     MSIM_DYN_SMEM(smem);
     const Lay& L = p.lay;
     const int lane = threadIdx.x & 31;

@@ -31,6 +31,7 @@ VARIANTS = {
     "duecache": ["MSIM_X_DUECACHE=1"],
     "ropecache": ["MSIM_X_ROPECACHE=1"],
     "nto_tailpush_flushgrp": ["MSIM_X_NTO=1", "MSIM_X_TAILPUSH=1", "MSIM_X_FLUSHGRP=1"],
+    "lb4": ["MSIM_X_MINBLOCKS=4"],        # 64 registers, no spills: meaningful for the smem-limited onDue part only
     "allx": ["MSIM_X_NTO=1", "MSIM_X_TAILPUSH=1", "MSIM_X_FLUSHGRP=1", "MSIM_X_DUECACHE=1", "MSIM_X_ROPECACHE=1"],
 }
 RESTRICTED = set()

@@ -50,7 +50,9 @@ for i, ((cfg, res, prod), policy, phase, period) in enumerate(spec["parts"]):
     mpo, mdo = spec.get("pools", [(0, 0)] * len(spec["parts"]))[i]
     t = compile_scenario(cfg, res, prod, policy=policy, dbr_repair=spec.get("dbr_repair", False),
                          max_production_orders=mpo, max_demand_orders=mdo)
-    eng = emu.EmuEngine(t, "cov", layout={layout!r})
+    if {part!r} is not None and i != {part!r}:
+        continue
+    eng = emu.EmuEngine(t, "cov", layout={layout!r}, defines={defines!r})
     r = eng.run({reps}, seed=20260101 + i, n_log_reps={reps}, log_cap=4096)
     assert (r.status == 0).all(), r.status
     events += int(r.n_events.sum())
@@ -59,20 +61,20 @@ print(json.dumps({{"events": events, "policy": spec["parts"][0][1]}}))
 """
 
 
-def run_coverage(layout, workload, run_until, reps):
+def run_coverage(layout, workload, run_until, reps, defines=(), part=None):
     import emu
 
-    emu.build("cov")
+    emu.build("cov", extra_defines=defines)
     for f in BUILD.glob("*.gcda"):
         f.unlink()
     code = RUNNER.format(root=str(ROOT), emu=str(ROOT / "tests" / "emu"), workload=workload, run_until=run_until,
-                         layout=layout, reps=reps)
+                         layout=layout, reps=reps, defines=tuple(defines), part=part)
     r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=3600,
                        env={**__import__("os").environ, "MSIM_EMU_THREADS": "1"})
     if r.returncode != 0:
         raise RuntimeError(r.stderr[-3000:])
     info = json.loads(r.stdout.strip().splitlines()[-1])
-    stem = Path(SRC[layout]).stem + "_cov"
+    stem = Path(SRC[layout]).stem + "_" + emu._tag("cov", tuple(defines))
     g = subprocess.run(["gcov", "--json-format", "--stdout", str(BUILD / f"{stem}.gcda")], capture_output=True,
                        text=True, cwd=str(BUILD))
     if g.returncode != 0:
@@ -94,12 +96,12 @@ def run_coverage(layout, workload, run_until, reps):
 
 
 # ----------------------------------------------------------------------------------------------- SASS with lines
-def sass_chains(layout, policy, rng=0):
+def sass_chains(layout, policy, rng=0, lib=None):
     tmp = BUILD / "cubin"
     tmp.mkdir(exist_ok=True)
     for f in tmp.glob("*.cubin"):
         f.unlink()
-    subprocess.run(["cuobjdump", "-xelf", "all", str(ROOT / "manusim_b200" / "libmsim.so")], cwd=str(tmp), check=True,
+    subprocess.run(["cuobjdump", "-xelf", "all", str(Path(lib).resolve() if lib else ROOT / "manusim_b200" / "libmsim.so")], cwd=str(tmp), check=True,
                    capture_output=True)
     cubin = tmp / (Path(SRC[layout]).stem + ".sm_100a.cubin")
     txt = subprocess.run(["nvdisasm", "-gi", "-c", str(cubin)], capture_output=True, text=True, check=True).stdout
@@ -207,12 +209,17 @@ def main():
     ap.add_argument("--reps", type=int, default=1)
     ap.add_argument("--top", type=int, default=25)
     ap.add_argument("--json", default=None)
+    ap.add_argument("--defines", default="", help="comma-separated experiment switches, e.g. MSIM_X_DUECACHE=1 "
+                                                   "(needs the matching nvcc build: --lib manusim_b200/libmsim_<tag>.so)")
+    ap.add_argument("--lib", default=None)
+    ap.add_argument("--part", type=int, default=None, help="only this part of the workload (jobshop20: 0 asReady, 1 onDue)")
     a = ap.parse_args()
+    defines = tuple(d for d in a.defines.split(",") if d)
 
-    info, lines, funcs = run_coverage(a.layout, a.workload, a.run_until, a.reps)
+    info, lines, funcs = run_coverage(a.layout, a.workload, a.run_until, a.reps, defines, a.part)
     src = SRC[a.layout]
     funcs = {name: function_ranges(ROOT / "manusim_b200" / "csrc" / name) for name in (src, "philox.cuh")}
-    chains = sass_chains(a.layout, info["policy"])
+    chains = sass_chains(a.layout, info["policy"], lib=a.lib)
     lane0, (k0, k1) = lane0_lines(ROOT / "manusim_b200" / "csrc" / src)
 
     def entries(fname, line):

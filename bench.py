@@ -376,6 +376,21 @@ def main():
     except Exception as exc:                                   # pragma: no cover
         roofline["kernel_by_part"] = f"unavailable: {exc!r}"
 
+    # the ceiling that actually bounds this path: warp-instruction issue slots = SMs x 4 schedulers x clock
+    try:
+        mhz = float((clocks or {}).get("sm_mhz") or 1965.0)
+        n_sms = parts[0]["eng"].info["n_sms"]
+        ceiling = n_sms * 4 * mhz * 1e6
+        ipe = 86.0
+        roofline["issue_slots"] = {
+            "ceiling_warp_instr_per_s": ceiling, "warp_instr_per_event": ipe,
+            "warp_instr_per_event_source": "ncu smsp__inst_executed.sum / SimPy events, SoA slab build "
+                                           "(profiles/README.md); not re-measured for the AoS default",
+            "busy_frac_estimate": (events / world) / (kern_ms * 1e-3) * ipe / ceiling if kern_ms > 0 else None,
+            "ncu_issue_active_frac": 0.399}
+    except Exception as exc:                                   # pragma: no cover
+        roofline["issue_slots"] = f"unavailable: {exc!r}"
+
     # ---- end to end through the public host-buffer API: pinned H2D of the step's inputs + D2H of its results
     def e2e_step(step):
         set_seeds(step)

@@ -16,7 +16,10 @@ independent lines into each other are ignored.  It is calibrated against the one
 the default kernel (86 warp instructions per SimPy event on jobshop20, profiles/README.md) and is meant for RELATIVE
 comparisons between kernel variants before GPU minutes are spent on them.
 
-usage: python tools/instr_model.py [--layout soa|aos] [--workload jobshop20|simple|dbr] [--run-until N] [--top K]
+usage: python tools/instr_model.py [--layout soa|aos] [--workload jobshop20|simple_det|toc_dbr] [--run-until N] [--top K]
+                                   [--part i] [--defines MSIM_X_...=1,... --lib manusim_b200/libmsim_<tag>.so]
+Track record: it mis-predicted the AoS slab (a code-SIZE effect: predicted ~0, measured +7 %); for changes that remove
+executed instructions from straight-line code (e.g. the onDue timer cache) it is the right tool.
 """
 from __future__ import annotations
 

@@ -133,6 +133,10 @@ enum { RM_UTIL = 0, RM_BREAKDOWN, RM_SETUP, RM_QUEUE };
 enum { GM_WIP = 0, GM_FG, GM_INV };
 
 __device__ __forceinline__ uint32_t EV(uint32_t op, uint32_t a, uint32_t b) { return op | (a << 8) | (b << 16); }
+// DBR only (python-typed clock): a Timeout whose delay is a numpy float32 makes Environment._now a
+// float32 when it is popped -- also when now + delay rounds back to `now` and the event therefore travels through the
+// NORMAL fifo instead of the calendar.  Bit 24 of the event word carries that "the clock becomes float32-typed" mark.
+constexpr uint32_t EV_F32 = 1u << 24;
 
 // round(np.float32 x, 6)  (factory_sim.py:284,443)
 __device__ __forceinline__ float round6(float x) { return __fdiv_rn(rintf(__fmul_rn(x, 1e6f)), 1e6f); }
@@ -236,9 +240,10 @@ struct Sim {
         if (uqt - uqh > (uint32_t)p.lay.UQ) fail(MSIM_ST_FIFO_OVERFLOW);
     }
     // env.timeout(delay) issued by a static process that owns calendar slot `slot`
-    __device__ __forceinline__ void timer(int slot, float t, uint32_t ev) {
+    // `f32`: the delay is float32-typed (false: python int, e.g. the warm-up instant or a zero setup)
+    __device__ __forceinline__ void timer(int slot, float t, uint32_t ev, bool f32 = true) {
         if (t == now) {
-            pushN(ev);   // lands on the current timestamp: larger eid than everything already pending
+            pushN(DBR && f32 ? ev | EV_F32 : ev);   // lands on the current timestamp: larger eid than everything already pending
         } else {
             ARR(float, tm_time)[slot] = t;
             ARR(uint32_t, tm_eid)[slot] = tseq++;
@@ -499,7 +504,7 @@ struct Sim {
         RES(float, start, r) = now;                                      // breakdown_start, :272
         float ttr = draw_scalar(3, TAB(DDist, t_ttr)[r]);                  // :275
         if (DBR) ARR(uint8_t, r_flags)[r] &= ~F_TIMER_PY;
-        timer(r, __fadd_rn(now, ttr), EV(OP_TO_TTR, r, 0));
+        timer(r, __fadd_rn(now, ttr), EV(OP_TO_TTR, r, 0), ttr > 0.0f);      // max(0, np.float32(v)) is the int 0 for v <= 0
     }
     // _production_system loop top   factory_sim.py:375-380
     __device__ __forceinline__ void mach_loop_top(int r) {
@@ -514,6 +519,7 @@ struct Sim {
 
     // ------------------------------------------------------------------ one micro-event
     __device__ __forceinline__ void dispatch(uint32_t ev) {
+        if (DBR && (ev & EV_F32)) now_py = 0;                    // popped Timeout with a float32-typed time
         const uint32_t op = ev & 0xFFu;
         int a = (ev >> 8) & 0xFF;
         int b = (ev >> 16) & 0xFF;
@@ -634,8 +640,10 @@ struct Sim {
             if (DBR) ARR(uint8_t, r_flags)[a] &= ~F_TIMER_PY;
             {
                 const float t = __fadd_rn(now, RES(float, setup, a));
-                if (t != now || !alone()) { timer(a, t, EV(OP_TO_SETUP, a, 0)); break; }
+                const bool f32 = (RES(float, setup, a) > 0.0f);                  // a positive setup is a numpy float32, a zero one the int 0
+                if (t != now || !alone()) { timer(a, t, EV(OP_TO_SETUP, a, 0), f32); break; }
                 nev++;                                           // Timeout(0): lands on this timestamp and is popped right away
+                if (DBR && f32) now_py = 0;                      // (a tiny positive setup can round back to `now`)
             }
             // fall through
         case OP_TO_SETUP:
@@ -840,7 +848,7 @@ struct Sim {
                 if (wait > 0.0f) {
                     float t = __fadd_rn(now, wait);
                     if (t == now) {
-                        pushN(EV(OP_TO_SHIP, a, b));
+                        pushN(DBR ? EV(OP_TO_SHIP, a, b) | EV_F32 : EV(OP_TO_SHIP, a, b));
                     } else {
                         ARR(float, do_tt)[b] = t;
 #if MSIM_X_DUECACHE
@@ -877,7 +885,7 @@ struct Sim {
                 if (sched > now) {
                     float t = __fadd_rn(now, __fsub_rn(sched, now));
                     if (t == now) {
-                        pushN(EV(OP_TO_DORDER, 0, b));
+                        pushN(EV(OP_TO_DORDER, 0, b) | EV_F32);
                     } else {
                         ARR(float, po_tt)[b] = t;
 #if MSIM_X_ROPECACHE
@@ -1046,7 +1054,7 @@ struct Sim {
             RES(float, tbf, r) = tb_.kind == MSIM_DIST_NONE ? CUDART_INF_F : draw_scalar(3, tb_);
         }
         nev++;                                                   // Initialize[warmup]
-        timer(R + P, p.warmup, EV(OP_TO_WARMUP, 0, 0));
+        timer(R + P, p.warmup, EV(OP_TO_WARMUP, 0, 0), false);
         for (int r = 0; r < R; ++r) {
             nev += 2;                                            // Initialize[_transportation], Initialize[_production_system]
             sc->trans_wait |= 1u << r;

@@ -117,6 +117,17 @@ def scenario_table():
     simd.update(run_until=1501, warmup=300, memory_size=200000, delivery_mode="onDue")
     out["dbr_ondue"] = dict(cfg=simd, resources=resd, products=prodd, policy="dbr", seed=280679,
                             patches=["P1", "P2", "P3"])
+    # python-typed clock vs float32 Timeouts that round back onto the current timestamp: positive setups far below the
+    # float32 spacing of the clock (1e-4 against 4.9e-4 beyond t = 4096) on every other resource, zero setups elsewhere;
+    # orders released at int-typed tick instants then meet `now + np.float32(1e-4) == now` with a clock that turns
+    # float32 (found at t = 128064 of the shipped horizon; the kernel kept the python type there before the fix)
+    simy, resy, prody, _ = _example("toc_dbr")
+    simy.pop("print_mode", None)
+    simy.update(run_until=7001, warmup=4200, memory_size=200000, scheduler_interval=24, cb_target_level=120)
+    for i, r in enumerate(resy.values()):
+        r["setup"] = {"dist": "constant", "params": [1e-4 if i % 2 == 0 else 0, 0]}
+    out["dbr_tiny_setup"] = dict(cfg=simy, resources=resy, products=prody, policy="dbr", seed=806309,
+                                 patches=["P2", "P3"])
     # SimPy ValueError cases: negative batch delay, Container.put(0)
     cfg, res, prod = sc.toy2(run_until=400)
     prod["p1"]["processes"]["s1"]["processing_time"] = {"dist": "uniform", "params": [0.2, 2.0]}   # a < 0

@@ -118,6 +118,7 @@ enum Op : uint32_t {
     OP_DELIV_GOT, OP_INIT_SHIP, OP_TO_SHIP, OP_SHIP_GOT,
     // DBR (examples/toc_dbr/simulation.py)
     OP_TO_TICK, OP_INIT_DORDER, OP_TO_DORDER, OP_SEED_PUT, OP_FIN_PUT, OP_DRAIN_GOT,
+    OP_HOP,   // not a SimPy event: re-queues itself b-1 more times, then queues TO_SETUP of resource a (see OP_MACH_REQ)
 };
 
 enum Loc : uint8_t { LOC_NONE = 0, LOC_IN = 1, LOC_PROC = 2, LOC_OUT = 3, LOC_TRANS = 4 };
@@ -635,16 +636,27 @@ struct Sim {
             nev++;                                               // Request popped right away
         }
         // fall through
-        case OP_MACH_REQ:                                        // :423
+        case OP_MACH_REQ: {                                      // :423
+            const uint32_t ahead = force;      // 1: MACH_GOT, PUTPROC and this event ran ahead of the transport chain
             force = 0;
             if (DBR) ARR(uint8_t, r_flags)[a] &= ~F_TIMER_PY;
             {
                 const float t = __fadd_rn(now, RES(float, setup, a));
                 const bool f32 = (RES(float, setup, a) > 0.0f);                  // a positive setup is a numpy float32, a zero one the int 0
+                if (ahead && t == now) {
+                    // The setup Timeout lands on the current timestamp, so the machine goes on within it -- and SimPy
+                    // schedules that Timeout only after the first three transport events (TRANS_GOT, TRANS_PUT,
+                    // GOT2_*) that this chain overtook.  OP_HOP re-queues itself behind each of them and then queues
+                    // TO_SETUP exactly where SimPy has it (found by long-horizon replays: a zero setup followed by a
+                    // zero-time operation emitted its utilisation record ahead of the transport chain's records).
+                    pushN(EV(OP_HOP, a, 3));
+                    break;
+                }
                 if (t != now || !alone()) { timer(a, t, EV(OP_TO_SETUP, a, 0), f32); break; }
                 nev++;                                           // Timeout(0): lands on this timestamp and is popped right away
                 if (DBR && f32) now_py = 0;                      // (a tiny positive setup can round back to `now`)
             }
+        }
             // fall through
         case OP_TO_SETUP:
         {                                      // :425-440
@@ -935,6 +947,10 @@ struct Sim {
                     sc->drain_wait = 1;
                 }
             }
+            break;
+        case OP_HOP:                                             // bookkeeping only, not an Environment.step()
+            nev--;
+            pushN(b > 1 ? EV(OP_HOP, a, b - 1) : EV(OP_TO_SETUP, a, 0));
             break;
         default:
             break;

@@ -128,6 +128,19 @@ def scenario_table():
         r["setup"] = {"dist": "constant", "params": [1e-4 if i % 2 == 0 else 0, 0]}
     out["dbr_tiny_setup"] = dict(cfg=simy, resources=resy, products=prody, policy="dbr", seed=806309,
                                  patches=["P2", "P3"])
+    # zero setups and zero-time operations under max-priority dispatch: the machine finishes whole operations inside one
+    # timestamp while the transport chain of the previous order is still being processed (event order within a
+    # timestamp; the kernel's "machine chain ahead of the transport chain" shortcut needed OP_HOP for this)
+    simz, resz, prodz, _ = _example("simple_scheduler")
+    simz.pop("print_mode", None)
+    simz.update(run_until=400, warmup=40, memory_size=100000)
+    for r in resz.values():
+        r["setup"] = {"dist": "constant", "params": [0, 0]}
+    for j, p_ in enumerate(prodz.values()):
+        for k, st in enumerate(p_["processes"].values()):
+            if (j + k) % 3 == 0:
+                st["processing_time"] = {"dist": "constant", "params": [0, 0]}
+    out["ss_zero_ops"] = dict(cfg=simz, resources=resz, products=prodz, policy="simple_scheduler", seed=91421, patches=[])
     # SimPy ValueError cases: negative batch delay, Container.put(0)
     cfg, res, prod = sc.toy2(run_until=400)
     prod["p1"]["processes"]["s1"]["processing_time"] = {"dist": "uniform", "params": [0.2, 2.0]}   # a < 0

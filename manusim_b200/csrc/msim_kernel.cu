@@ -68,10 +68,11 @@ enum { RM_UTIL = 0, RM_BREAKDOWN, RM_SETUP, RM_QUEUE };
 enum { GM_WIP = 0, GM_FG, GM_INV };
 
 __device__ __forceinline__ uint32_t EV(uint32_t op, uint32_t a, uint32_t b) { return op | (a << 8) | (b << 16); }
-// DBR only (python-typed clock): a Timeout whose delay is a numpy float32 makes Environment._now a
-// float32 when it is popped -- also when now + delay rounds back to `now` and the event therefore travels through the
-// NORMAL fifo instead of the calendar.  Bit 24 of the event word carries that "the clock becomes float32-typed" mark.
-constexpr uint32_t EV_F32 = 1u << 24;
+// DBR only (python-typed clock): Environment.step() sets _now to the popped entry's own time
+// OBJECT, so the clock's type is a property of every queued event -- an event scheduled with the default delay 0
+// inherits the type the clock had when it was scheduled, a Timeout with a numpy float32 delay is float32-typed even
+// when now + delay rounds back to `now`.  Bit 24 of the event word: the clock is python-typed when this event pops.
+constexpr uint32_t EV_PY = 1u << 24;
 
 // round(np.float32 x, 6)  (factory_sim.py:284,443)
 __device__ __forceinline__ float round6(float x) { return __fdiv_rn(rintf(__fmul_rn(x, 1e6f)), 1e6f); }
@@ -164,11 +165,13 @@ struct Sim {
     __device__ __forceinline__ void fail(int code) { status = code; attn |= A_STATUS; }
 
     // ------------------------------------------------------------------ event queues
-    __device__ __forceinline__ void pushN(uint32_t ev) {
+    __device__ __forceinline__ void pushN_raw(uint32_t ev) {
         ARR(uint32_t, nq)[nqt & (uint32_t)(p.lay.NQ - 1)] = ev;
         nqt++;       // overflow is checked once per dispatched event (drain); the ring index is masked, so a
     }                // transient overrun stays inside the slab and aborts the replication with a status code
+    __device__ __forceinline__ void pushN(uint32_t ev) { pushN_raw(DBR ? ev | (now_py << 24) : ev); }   // inherits the clock type
     __device__ __forceinline__ void pushU(uint32_t ev) {
+        if (DBR) ev |= now_py << 24;
         ARR(uint32_t, uq)[uqt & (uint32_t)(p.lay.UQ - 1)] = ev;
         uqt++;
         attn |= A_URGENT;
@@ -178,7 +181,7 @@ struct Sim {
     // `f32`: the delay is float32-typed (false: python int, e.g. the warm-up instant or a zero setup)
     __device__ __forceinline__ void timer(int slot, float t, uint32_t ev, bool f32 = true) {
         if (t == now) {
-            pushN(DBR && f32 ? ev | EV_F32 : ev);   // lands on the current timestamp: larger eid than everything already pending
+            if (DBR && f32) pushN_raw(ev); else pushN(ev);   // lands on the current timestamp: larger eid than everything pending
         } else {
             ARR(float, tm_time)[slot] = t;
             ARR(uint32_t, tm_eid)[slot] = tseq++;
@@ -456,7 +459,7 @@ struct Sim {
 
     // ------------------------------------------------------------------ one micro-event
     __device__ __forceinline__ void dispatch(uint32_t ev) {
-        if (DBR && (ev & EV_F32)) now_py = 0;                    // popped Timeout with a float32-typed time
+        if (DBR) now_py = (ev >> 24) & 1u;                       // _now takes the popped entry's type
         const uint32_t op = ev & 0xFFu;
         int a = (ev >> 8) & 0xFF;
         int b = (ev >> 16) & 0xFF;
@@ -791,7 +794,7 @@ struct Sim {
                 if (wait > 0.0f) {
                     float t = __fadd_rn(now, wait);
                     if (t == now) {
-                        pushN(DBR ? EV(OP_TO_SHIP, a, b) | EV_F32 : EV(OP_TO_SHIP, a, b));
+                        pushN_raw(EV(OP_TO_SHIP, a, b));          // float32-typed Timeout (due - now)
                     } else {
                         ARR(float, do_tt)[b] = t;
                         ARR(uint32_t, do_eid)[b] = tseq++;
@@ -821,7 +824,7 @@ struct Sim {
                 if (sched > now) {
                     float t = __fadd_rn(now, __fsub_rn(sched, now));
                     if (t == now) {
-                        pushN(EV(OP_TO_DORDER, 0, b) | EV_F32);
+                        pushN_raw(EV(OP_TO_DORDER, 0, b));        // float32-typed Timeout (schedule - now)
                     } else {
                         ARR(float, po_tt)[b] = t;
                         ARR(uint32_t, po_eid)[b] = tseq++;
@@ -1004,7 +1007,7 @@ struct Sim {
                 ARR(float, p_fg)[prod] = sbuf;
                 pushN(EV(OP_SEED_PUT, prod, 0));
             }
-            pending = EV(OP_TO_TICK, 0, 0); attn |= A_PENDING;   // Initialize[scheduler] (the rope): first tick at t = 0,
+            pending = EV(OP_TO_TICK, 0, 0) | EV_PY; attn |= A_PENDING;   // Initialize[scheduler] (the rope): first tick at t = 0,
             return;                                              // counted and executed by dispatch before any NORMAL event
         }
         nev++;                                                   // Initialize[scheduler]
@@ -1264,7 +1267,7 @@ __global__ void __launch_bounds__(256, 5) sim_kernel(const __grid_constant__ KPa
                     ev = EV(OP_TO_DORDER, 0, po);
                     reinterpret_cast<float*>(sb + L.po_tt)[po] = CUDART_INF_F;
                 }
-                first_ev = ev;
+                first_ev = DBR ? ev | (s.now_py << 24) : ev;
             }
             __syncwarp();
         }

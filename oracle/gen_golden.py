@@ -128,6 +128,12 @@ def scenario_table():
         r["setup"] = {"dist": "constant", "params": [1e-4 if i % 2 == 0 else 0, 0]}
     out["dbr_tiny_setup"] = dict(cfg=simy, resources=resy, products=prody, policy="dbr", seed=806309,
                                  patches=["P2", "P3"])
+    # calendar entries of different clock types tied at one float32 instant: the events each of them schedules keep
+    # their creator's type (Environment.step() takes _now from the popped entry); same stress configuration as
+    # dbr_typed, a seed and horizon where the kernel of the round-1 GPU runs logged a float64-path utilisation at
+    # t = 2184.97 (42 differing records up to t = 2301)
+    out["dbr_mixed_types"] = dict(cfg=dict(sim_t, run_until=2401, warmup=100), resources=res_t, products=prod,
+                                  policy="dbr", seed=4242, patches=["P2", "P3"])
     # zero setups and zero-time operations under max-priority dispatch: the machine finishes whole operations inside one
     # timestamp while the transport chain of the previous order is still being processed (event order within a
     # timestamp; the kernel's "machine chain ahead of the transport chain" shortcut needed OP_HOP for this)

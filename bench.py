@@ -128,6 +128,7 @@ class ClockSampler:
 # --------------------------------------------------------------------------------------------- CPU side
 def _oracle_one(task):
     spec_name, run_until, part_idx, seed = task
+    os.environ.setdefault("ORACLE_SIMPY", "auto")          # the real SimPy package when importable, else the restatement
     from oracle.factory_oracle import FactoryOracle
 
     spec = workload_spec(spec_name, run_until)
@@ -146,6 +147,25 @@ def cpu_pool_pass(pool, spec_name, run_until, n_parts, seeds):
     wall = time.perf_counter() - t0
     events = sum(o[0] for o in outs)
     return events, wall, sum(o[1] for o in outs)
+
+
+def cpu_baseline_meta():
+    """What the CPU arm is: the oracle PORT of the reference's model (the unmodified reference needs /root/reference and
+    cannot travel to the GPU box) on the best SimPy layer importable here, plus the calibration of that port against the
+    UNMODIFIED reference measured in the build container (tools/cpu_calibration.py -> profiles/cpu_calibration.json)."""
+    os.environ.setdefault("ORACLE_SIMPY", "auto")
+    from oracle.factory_oracle import SIMPY_ENGINE
+
+    meta = {"kind": "port", "engine": f"oracle/factory_oracle.py on {SIMPY_ENGINE}"}
+    try:
+        c = json.loads((ROOT / "profiles" / "cpu_calibration.json").read_text())
+        meta["calibration"] = {"port_over_unmodified_reference": c["port_over_reference"],
+                               "unmodified_reference_events_per_s_per_core": c["unmodified_reference_events_per_s_per_core"],
+                               "port_events_per_s_per_core": c["port_events_per_s_per_core"],
+                               "source": "profiles/cpu_calibration.json (build container, one core, same seeds)"}
+    except Exception:
+        meta["calibration"] = None
+    return meta
 
 
 def reference_arm(args):
@@ -182,14 +202,25 @@ def reference_arm(args):
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": spec["desc"], "replications_per_step": per_step, "l2": "n/a (CPU)"},
             "replications_per_sec": per_step * args.steps / wall,
-            "cpu_baseline": {"value": value, "unit": "events/s", "cores": workers, "kind": "port", "sample": sample,
-                             "engine": "oracle/factory_oracle.py on oracle/minisimpy.py (SimPy 4.1.1 restated; "
-                                       "real SimPy is not installable offline)"},
+            "cpu_baseline": dict(cpu_baseline_meta(), value=value, unit="events/s", cores=workers, sample=sample),
             "e2e": {"value": value, "unit": "events/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
 
 
 # --------------------------------------------------------------------------------------------- GPU arm
+COUNTERS = ROOT / "profiles" / "kernel_counters.json"
+
+
+def load_counters(workload):
+    """ncu-derived per-kernel counters committed under profiles/ (written by tools/summarize_profiles.py from the
+    `ncu --set full` capture named inside the file).  Absent file or workload => None: the bench never invents them."""
+    try:
+        d = json.loads(COUNTERS.read_text())
+        return d["workloads"][workload], d.get("source")
+    except Exception:
+        return None, None
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -197,7 +228,11 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="jobshop20")
-    ap.add_argument("--reps", type=int, default=16384, help="replications per GPU per step")
+    ap.add_argument("--reps", type=int, default=0,
+                    help="replications per GPU per step (0 = `--waves` full waves of the resident replications)")
+    ap.add_argument("--waves", type=float, default=2.0,
+                    help="with --reps 0: replications per part = waves x (resident warps per SM x SMs) of its kernel, "
+                         "the same count for every part (the largest)")
     ap.add_argument("--run-until", type=int, default=None)
     ap.add_argument("--log-cap", type=int, default=4096, help="records per replication HBM ring (0 = no log streaming)")
     ap.add_argument("--cpu-workers", type=int, default=0)
@@ -205,6 +240,9 @@ def main():
     ap.add_argument("--max-do", type=int, default=0, help="demand-order pool per replication (0 = library default)")
     ap.add_argument("--fifo", type=int, default=0, help="zero-delay event ring capacity (0 = library default)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true", help="skip the end-to-end leg (profiling runs)")
+    ap.add_argument("--serial-parts", action="store_true", help="launch the workload parts one after the other on one "
+                    "stream (default: one stream per part, so one part's tail wave overlaps the next part's body)")
     ap.add_argument("--no-retry", action="store_true", help="do not re-run pool-overflow replications with big pools")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
@@ -234,8 +272,15 @@ def main():
         eng = BatchEngine(compile_scenario(cfg, res, prod, policy=policy, dbr_repair=spec.get("dbr_repair", False),
                                            max_production_orders=args.max_po or mpo,
                                            max_demand_orders=args.max_do or mdo, fifo_capacity=args.fifo))
-        n = args.reps // period
-        parts.append({"eng": eng, "n": n, "phase": phase, "period": period})
+        resident = eng.info["warps_per_block"] * eng.info["blocks_per_sm"] * eng.info["n_sms"]
+        parts.append({"eng": eng, "phase": phase, "period": period, "resident": resident})
+    if args.reps > 0:
+        reps = args.reps
+    else:
+        # every part simulates the same number of replications (the workload alternates them by index parity)
+        reps = int(round(args.waves * max(p["resident"] for p in parts))) * max(p["period"] for p in parts)
+    for p in parts:
+        p["n"] = reps // p["period"]
     K = parts[0]["eng"].K
     n_total_rank = sum(p["n"] for p in parts)
     log_cap = args.log_cap
@@ -246,35 +291,48 @@ def main():
         p["seeds_dev"] = torch.empty((p["n"],), dtype=torch.int64, device=dev)
         p["ev_part"] = torch.zeros((), dtype=torch.int64, device=dev)      # events of this part over the timed steps
     stats = torch.zeros((K, 3), dtype=torch.float64, device=dev)
+    stats_host = torch.zeros((K, 3), dtype=torch.float64).pin_memory()
     ev_total = torch.zeros((), dtype=torch.int64, device=dev)
     fail_total = torch.zeros((), dtype=torch.int64, device=dev)
     fail_codes = torch.zeros((9,), dtype=torch.int64, device=dev)
     rec_total = torch.zeros((), dtype=torch.int64, device=dev)
     flush_buf = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)   # > 126 MB L2
     stream = torch.cuda.current_stream(dev)
+    part_streams = [stream if args.serial_parts else torch.cuda.Stream(dev) for _ in parts]
     side = [torch.cuda.Stream(dev) for _ in parts]
 
     def set_seeds(step):
         for p in parts:
-            gidx = (np.arange(p["n"], dtype=np.int64) * p["period"] + p["phase"] + rank * args.reps)
+            gidx = (np.arange(p["n"], dtype=np.int64) * p["period"] + p["phase"] + rank * reps)
             keys = rep_keys(BASE_SEED + step, gidx)
             p["seeds_host"].copy_(torch.from_numpy(keys.view(np.int64)))
 
     sim_events = []
     retried = [0, 0]
+    launches = [0]
 
     def device_step(step, timed):
         set_seeds(step)
         stats.zero_()
-        for p in parts:
-            p["seeds_dev"].copy_(p["seeds_host"], non_blocking=True)
-            e0 = torch.cuda.Event(enable_timing=True)
-            e1 = torch.cuda.Event(enable_timing=True)
-            e0.record(stream)
-            p["eng"].run(p["n"], rep_seeds=p["seeds_dev"], out=p["res"], stream=stream)
-            e1.record(stream)
+        fork = torch.cuda.Event()
+        fork.record(stream)
+        for p, ps in zip(parts, part_streams):
+            ps.wait_event(fork)
+            with torch.cuda.stream(ps):
+                p["seeds_dev"].copy_(p["seeds_host"], non_blocking=True)
+                e0 = torch.cuda.Event(enable_timing=True)
+                e1 = torch.cuda.Event(enable_timing=True)
+                e0.record(ps)
+                p["eng"].run(p["n"], rep_seeds=p["seeds_dev"], out=p["res"], stream=ps)
+                e1.record(ps)
+            launches[0] += timed
             if timed:
-                sim_events.append((e0, e1, p))
+                sim_events.append((e0, e1, p, step))
+        for ps in part_streams:
+            if ps is not stream:
+                j = torch.cuda.Event()
+                j.record(ps)
+                stream.wait_event(j)
         if not args.no_retry:
             # congested replications that overflowed the shared-memory pools are re-run on a big-pool twin engine;
             # the (few, long) re-runs of all parts overlap on side streams
@@ -285,6 +343,7 @@ def main():
                     retried[1] += 1
         for p in parts:
             p["eng"].reduce(p["res"], out=stats, stream=stream)
+            launches[0] += timed
         if world > 1:
             dist.all_reduce(stats)
         if timed:
@@ -318,7 +377,6 @@ def main():
         s1.record(stream)
         torch.cuda.synchronize()
         step_ms.append(s0.elapsed_time(s1))
-    clocks = sampler.stop() if rank == 0 else None
     total_ms = float(sum(step_ms))
     t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
     ev = ev_total.clone()
@@ -330,9 +388,14 @@ def main():
     value = events / (total_ms * 1e-3)
     reps_total = n_total_rank * world * args.steps
 
-    # dominant kernel: the simulation kernel(s); algorithmic bytes per SURVEY 8(d)
-    kern_ms = sum(e0.elapsed_time(e1) for e0, e1, _ in sim_events)
+    # dominant kernel: the simulation kernel(s); algorithmic bytes per SURVEY 8(d).  With one stream per part the
+    # kernels of a step overlap, so the kernel time of a step is the span from the first start to the last end.
     n_launch = len(sim_events)
+    kern_ms = 0.0
+    for st in sorted({s for _, _, _, s in sim_events}):
+        evs = [(e0, e1) for e0, e1, _, s in sim_events if s == st]
+        first = evs[0][0]
+        kern_ms += max(first.elapsed_time(e1) for _, e1 in evs) - min(first.elapsed_time(e0) for e0, _ in evs)
     records_rank = int(rec_total.item())
     alg_bytes = 8 * records_rank + (16 * K + 8) * n_total_rank * args.steps
     peaks_file = ROOT / "MEASURED_PEAKS.json"
@@ -342,22 +405,20 @@ def main():
     else:
         peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
     achieved = alg_bytes / (kern_ms * 1e-3) / 1e9
-    # DRAM traffic per algorithmic byte measured once with `ncu --set full` (profiles/r01_ncu_full_final.csv:
-    # dram read 0.109 GB + write 4.624 GB for 2.341 GB algorithmic): records are streamed as 16-byte slots, twice the
-    # 8 bytes the reference's (time,value) float32 pair needs
-    traffic_per_alg_byte = 2.02 if log_cap else None
+    counters, counters_src = load_counters(args.workload)
+    dram_ratio = (counters or {}).get("dram_bytes_per_algorithmic_byte") if log_cap else None
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": (traffic_per_alg_byte * alg_bytes / max(n_launch, 1)) if traffic_per_alg_byte else None,
-                "traffic_source": "ncu dram__bytes_read.sum+dram__bytes_write.sum of one --set full capture, scaled by "
-                                  "algorithmic bytes (profiles/r01_ncu_full_final.csv)",
+                "traffic": (dram_ratio * alg_bytes / max(n_launch, 1)) if dram_ratio else None,
+                "traffic_source": (f"{COUNTERS.relative_to(ROOT)}: dram__bytes_read.sum + dram__bytes_write.sum per "
+                                   f"algorithmic byte of the capture named there ({counters_src}), times this run's "
+                                   f"algorithmic bytes per launch") if dram_ratio else None,
                 "peak_source": peak_src,
-                "kernel": ("msim::sim_kernel<policy,rng>" if os.environ.get("MSIM_SLAB_LAYOUT") == "soa"
-                           else "msim::aos::sim_kernel<policy,rng,opts>"),
+                "kernel": "msim::sim_kernel<policy,rng,opts,minb>",
                 "kernel_ms_per_launch": kern_ms / max(n_launch, 1), "launches": n_launch,
+                "kernel_ms_note": "span of the overlapping per-part launches of a step / launches" if not args.serial_parts
+                                  else "serial launches",
                 "algorithmic_bytes_per_launch": alg_bytes / max(n_launch, 1),
-                "note": "path is instruction-fetch / issue bound, not HBM bound (SURVEY 8(d)): 86 warp instructions per "
-                        "SimPy event, issue slots 40 % busy, stall_no_instruction dominant (ncu capture of the SoA "
-                        "slab build, profiles/README.md; the AoS slab that is now the default was A/B-timed only)",
+                "note": "path is instruction-fetch / issue bound, not HBM bound (SURVEY 8(d)); see issue_slots",
                 "kernel_share_of_step": kern_ms / sum(step_ms)}
 
     # per workload part (e.g. the asReady and the onDue half of jobshop20): simulation-kernel time and events/s of this
@@ -365,73 +426,100 @@ def main():
     try:
         by_part = []
         for i, p in enumerate(parts):
-            ms = sum(e0.elapsed_time(e1) for e0, e1, q in sim_events if q is p)
+            ms = sum(e0.elapsed_time(e1) for e0, e1, q, _ in sim_events if q is p)
             evp = int(p["ev_part"].item())
+            recp = int(p["res"].acc_cnt.sum(dtype=torch.int64).item())      # records of the last launch of this part
             by_part.append({"part": i, "delivery_mode": spec["parts"][i][0][0].get("delivery_mode"),
                             "replications_per_launch": p["n"], "kernel_ms_total": ms,
-                            "events_per_s": evp / (ms * 1e-3) if ms > 0 else None,
+                            "events_per_launch": evp / args.steps,
+                            "algorithmic_bytes_per_launch": 8 * recp + (16 * K + 8) * p["n"],
+                            "events_per_s_while_resident": evp / (ms * 1e-3) if ms > 0 else None,
                             "warps_per_sm": p["eng"].info["warps_per_block"] * p["eng"].info["blocks_per_sm"],
-                            "smem_per_replication": p["eng"].info["smem_per_replication"]})
+                            "waves": p["n"] / p["resident"],
+                            "smem_per_replication": p["eng"].info["smem_per_replication"],
+                            "regs_per_thread": p["eng"].info["regs_per_thread"]})
         roofline["kernel_by_part"] = by_part
+        if not args.serial_parts and len(parts) > 1:
+            roofline["kernel_by_part_note"] = ("the parts run concurrently (one stream each): a part's kernel_ms covers the "
+                                               "time it shares the SMs with the others")
     except Exception as exc:                                   # pragma: no cover
         roofline["kernel_by_part"] = f"unavailable: {exc!r}"
 
     # the ceiling that actually bounds this path: warp-instruction issue slots = SMs x 4 schedulers x clock
+    clocks = sampler.stop() if rank == 0 else None
     try:
         mhz = float((clocks or {}).get("sm_mhz") or 1965.0)
         n_sms = parts[0]["eng"].info["n_sms"]
         ceiling = n_sms * 4 * mhz * 1e6
-        ipe = 86.0
+        ipe = (counters or {}).get("warp_instr_per_event")
         roofline["issue_slots"] = {
             "ceiling_warp_instr_per_s": ceiling, "warp_instr_per_event": ipe,
-            "warp_instr_per_event_source": "ncu smsp__inst_executed.sum / SimPy events, SoA slab build "
-                                           "(profiles/README.md); not re-measured for the AoS default",
-            "busy_frac_estimate": (events / world) / (kern_ms * 1e-3) * ipe / ceiling if kern_ms > 0 else None,
-            "ncu_issue_active_frac": 0.399}
+            "busy_frac_estimate": ((events / world) / (kern_ms * 1e-3) * ipe / ceiling) if (ipe and kern_ms > 0) else None,
+            "ncu_issue_active_frac": (counters or {}).get("issue_active_frac"),
+            "ncu_lanes_per_instruction": (counters or {}).get("lanes_per_instruction"),
+            "ncu_stall_no_instruction_per_issue": (counters or {}).get("stall_no_instruction_per_issue"),
+            "source": (f"{COUNTERS.relative_to(ROOT)} ({counters_src})" if counters else None)}
     except Exception as exc:                                   # pragma: no cover
         roofline["issue_slots"] = f"unavailable: {exc!r}"
 
-    # ---- end to end through the public host-buffer API: pinned H2D of the step's inputs + D2H of its results
-    def e2e_step(step):
-        set_seeds(step)
-        tot = 0
-        for p in parts:
-            out = p["eng"].run_host(p["n"], rep_seeds=p["seeds_host"], out=p["host"])
-            tot += int(out.n_events.sum())
-        return tot
+    # ---- end to end through the public host-buffer API, the SAME step as above: pinned H2D of the step's inputs
+    # (replication keys), the simulation with its HBM log rings, the re-run of overflowed replications, the per-ring
+    # reduction, the allreduce (N > 1) and the D2H of the per-replication accumulators and of the statistics vector
+    e2e = None
+    if not args.no_e2e:
+        def e2e_step(step):
+            set_seeds(step)
+            stats.zero_()
+            tot = 0
+            for p in parts:
+                out = p["eng"].run_host(p["n"], rep_seeds=p["seeds_host"], out=p["host"],
+                                        device_log=p["res"] if log_cap else None, stats=stats,
+                                        retry_overflow=not args.no_retry)
+                tot += int(out.n_events.sum())
+            if world > 1:
+                dist.all_reduce(stats)
+            stats_host.copy_(stats, non_blocking=True)
+            torch.cuda.synchronize()
+            return tot
 
-    e2e_step(0)
-    torch.cuda.synchronize()
-    if world > 1:
-        dist.barrier()
-    t0 = time.perf_counter()
-    e2e_events = 0
-    e2e_steps = min(args.steps, 3)            # same step, fewer repetitions: keeps the default run within minutes
-    for k in range(e2e_steps):
-        e2e_events += e2e_step(args.warmup + k)
-    torch.cuda.synchronize()
-    e2e_s = time.perf_counter() - t0
-    t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
-    ev = torch.tensor([e2e_events], dtype=torch.int64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        dist.all_reduce(ev)
-    e2e_value = int(ev.item()) / float(t.item())
-    h2d = n_total_rank * 8 * world
-    d2h = n_total_rank * (K * 12 + 8 + 4 + 4) * world
+        for w in range(max(1, min(args.warmup, 2))):
+            e2e_step(w)
+        torch.cuda.synchronize()
+        e2e_events = 0
+        e2e_s = 0.0
+        for k in range(args.steps):
+            flush_buf.fill_(k & 0xFF)
+            torch.cuda.synchronize()
+            if world > 1:
+                dist.barrier()
+            t0 = time.perf_counter()
+            e2e_events += e2e_step(args.warmup + k)
+            e2e_s += time.perf_counter() - t0
+        t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+        ev = torch.tensor([e2e_events], dtype=torch.int64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dist.all_reduce(ev)
+        e2e = {"value": int(ev.item()) / float(t.item()), "unit": "events/s",
+               "h2d_bytes_per_step": n_total_rank * 8 * world,
+               "d2h_bytes_per_step": (n_total_rank * (K * 12 + 8 + 4 + 4) + K * 24) * world,
+               "steps": args.steps, "logs": f"device rings of {log_cap} records per replication, as in `value`" if log_cap else "off",
+               "api": "BatchEngine.run_host -> msim_run_host (pinned host buffers; log rings stay in HBM) "
+                      "+ per-ring reduction" + (" + NCCL allreduce" if world > 1 else ""),
+               "note": "host-buffer calls are synchronous, so the workload parts run one after the other here"}
 
-    line = {"metric": "simulated_events_per_sec", "value": value, "unit": "events/s", "n_gpus": world,
+    line = {"_cmd": "python bench.py " + " ".join(sys.argv[1:]),
+            "metric": "simulated_events_per_sec", "value": value, "unit": "events/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": total_ms / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": spec["desc"], "replications_per_gpu_per_step": n_total_rank,
                        "rng": "philox4x32-10", "log_ring_records_per_replication": log_cap,
-                       "slab_layout": os.environ.get("MSIM_SLAB_LAYOUT", "aos"),
+                       "parts": "concurrent streams" if not args.serial_parts else "serial",
                        "l2": "flushed with a 256 MB write between timed steps"},
             "replications_per_sec": reps_total / (total_ms * 1e-3),
             "events_per_replication": events / reps_total,
-            "e2e": {"value": e2e_value, "unit": "events/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "steps": e2e_steps, "api": "BatchEngine.run_host -> msim_run_host (pinned host buffers)"},
-            "gpu_launches": (2 * len(parts)) * args.steps + retried[1],
+            "e2e": e2e,
+            "gpu_launches": launches[0] + retried[1],
             "failed_replications": int(fail_total.item()),
             "pool_overflow_replications_rerun": retried[0],
             "status_histogram": fail_codes.tolist(),
@@ -450,10 +538,10 @@ def main():
             seeds = run_seeds(BASE_SEED, workers)
             with ProcessPoolExecutor(max_workers=workers) as pool:
                 e, wall, _ = cpu_pool_pass(pool, args.workload, args.run_until, len(spec["parts"]), seeds)
-            line["cpu_baseline"] = {"value": e / wall, "unit": "events/s", "cores": workers, "kind": "port",
-                                    "sample": f"{workers} full-length replications of the same workload, one per "
-                                              f"worker process ({wall:.1f} s wall)",
-                                    "replications_per_sec": workers / wall}
+            line["cpu_baseline"] = dict(cpu_baseline_meta(), value=e / wall, unit="events/s", cores=workers,
+                                        sample=f"{workers} full-length replications of the same workload, one per "
+                                               f"worker process ({wall:.1f} s wall)",
+                                        replications_per_sec=workers / wall)
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()

@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define MSIM_VERSION 100 /* 0.1.0 */
+#define MSIM_VERSION 200 /* 0.2.0 */
 
 /* distribution kinds -- DistributionGenerator.random_number, src/manusim/engine/utils.py:42-67 */
 enum { MSIM_DIST_NONE = -1, MSIM_DIST_CONSTANT = 0, MSIM_DIST_UNIFORM = 1, MSIM_DIST_GAMMA = 2,
@@ -82,17 +82,15 @@ typedef struct msim_tables {
     const msim_dist_t* prod_qty;     /* [P] demand.quantity */
     const msim_dist_t* prod_due;     /* [P] demand.duedate */
     const double* prod_shipping_buffer; /* [P] (DBR), may be NULL */
-    double run_until;
+    double run_until;                /* python numbers in the reference's config (int or float; the clock reaches them
+                                        as python-typed instants) */
     double warmup;
-    int32_t run_until_is_int;        /* python typing of run_until/warmup */
-    int32_t warmup_is_int;
     int32_t delivery_mode;           /* MSIM_DELIVERY_* */
     int32_t policy;                  /* MSIM_POLICY_* */
     int32_t log_queues;              /* factory_sim.py:53 */
     /* DBR parameters (examples/toc_dbr/simulation.py:29-32, 146-171, 201-204) */
     int32_t dbr_ccr;                 /* constraint resource index */
     int32_t dbr_repair;              /* oracle patch P3: feed resource_finished[CCR] */
-    int32_t dbr_interval_is_int;
     double dbr_interval, dbr_cb_target, dbr_release_limit, dbr_ccr_limit, dbr_min_lot, dbr_ccr_setup;
     const double* dbr_ccr_pt;        /* [P] sum of mean processing time on the CCR */
     /* capacities of the per-replication shared-memory pools (0 => defaults) */
@@ -140,8 +138,8 @@ typedef struct msim_run_args {
     void* stream;                    /* cudaStream_t (NULL = default stream) */
 } msim_run_args_t;
 
-/* Host-buffer twin used for the end-to-end path: all pointers are HOST memory (pinned or pageable);
- * the call stages tapes/seeds H2D, runs, copies the outputs D2H and synchronises. */
+/* Host-buffer twin used for the end-to-end path: all pointers are HOST memory (pinned or pageable) unless their
+ * name ends in _dev; the call stages tapes/seeds H2D, runs, copies the outputs D2H and synchronises. */
 typedef struct msim_host_args {
     int64_t n_reps;
     int64_t rep_offset;
@@ -156,6 +154,12 @@ typedef struct msim_host_args {
     double* acc_sum; uint32_t* acc_cnt; uint64_t* n_events; uint32_t* n_timeouts; int32_t* status;
     msim_record_t* log; uint32_t* log_count; int64_t log_cap; int64_t n_log_reps;
     double* kernel_ms;               /* optional out: device time of the simulation kernel */
+    /* optional DEVICE buffers (caller-allocated): record rings that stay in HBM -- replications [0, n_log_reps_dev)
+       stream their records exactly as in msim_run, nothing of them is copied back -- and the per-ring experiment
+       statistics of this call, accumulated into stats_dev [K][3] like msim_reduce_metrics (what the ranks allreduce).
+       `log` (host) and `log_dev` are mutually exclusive. */
+    msim_record_t* log_dev; uint32_t* log_count_dev; int64_t log_cap_dev; int64_t n_log_reps_dev;
+    double* stats_dev;
 } msim_host_args_t;
 
 typedef struct msim_info {

@@ -28,9 +28,8 @@ class Tables(C.Structure):
         ("res_ttr", C.POINTER(Dist)), ("prod_freq", C.POINTER(Dist)), ("prod_qty", C.POINTER(Dist)),
         ("prod_due", C.POINTER(Dist)), ("prod_shipping_buffer", C.POINTER(C.c_double)),
         ("run_until", C.c_double), ("warmup", C.c_double),
-        ("run_until_is_int", C.c_int32), ("warmup_is_int", C.c_int32),
         ("delivery_mode", C.c_int32), ("policy", C.c_int32), ("log_queues", C.c_int32),
-        ("dbr_ccr", C.c_int32), ("dbr_repair", C.c_int32), ("dbr_interval_is_int", C.c_int32),
+        ("dbr_ccr", C.c_int32), ("dbr_repair", C.c_int32),
         ("dbr_interval", C.c_double), ("dbr_cb_target", C.c_double), ("dbr_release_limit", C.c_double),
         ("dbr_ccr_limit", C.c_double), ("dbr_min_lot", C.c_double), ("dbr_ccr_setup", C.c_double),
         ("dbr_ccr_pt", C.POINTER(C.c_double)),
@@ -61,6 +60,8 @@ class HostArgs(C.Structure):
         ("acc_sum", C.c_void_p), ("acc_cnt", C.c_void_p), ("n_events", C.c_void_p), ("n_timeouts", C.c_void_p),
         ("status", C.c_void_p), ("log", C.c_void_p), ("log_count", C.c_void_p), ("log_cap", C.c_int64),
         ("n_log_reps", C.c_int64), ("kernel_ms", C.POINTER(C.c_double)),
+        ("log_dev", C.c_void_p), ("log_count_dev", C.c_void_p), ("log_cap_dev", C.c_int64),
+        ("n_log_reps_dev", C.c_int64), ("stats_dev", C.c_void_p),
     ]
 
 

@@ -9,7 +9,7 @@ from pathlib import Path
 PKG = Path(__file__).resolve().parent
 CSRC = PKG / "csrc"
 LIB = PKG / "libmsim.so"
-SOURCES = ["msim_kernel.cu", "msim_kernel_aos.cu", "msim_api.cu"]
+SOURCES = ["msim_kernel.cu", "msim_reduce.cu", "msim_api.cu"]
 HEADERS = ["msim_device.cuh", "philox.cuh", "../../include/msim.h"]
 
 
@@ -34,8 +34,8 @@ def variant_path(tag: str) -> Path:
 
 
 def build_lib(force: bool = False, verbose: bool = False, defines=(), tag: str = "") -> Path:
-    """One nvcc per translation unit (in parallel), then one link: libmsim.so holds the simulation kernel in its two
-    slab layouts (msim_kernel_aos.cu = default, msim_kernel.cu = MSIM_SLAB_LAYOUT=soa) and the C ABI (msim_api.cu).
+    """One nvcc per translation unit (in parallel), then one link: libmsim.so holds the simulation kernel
+    (msim_kernel.cu), the experiment-statistics reductions (msim_reduce.cu) and the C ABI (msim_api.cu).
     `tag` + `defines` build an experiment variant next to it (libmsim_<tag>.so)."""
     LIB = variant_path(tag) if tag else globals()["LIB"]
     if not force and not tag and not needs_build():

@@ -26,11 +26,11 @@ static int fail(int code, const std::string& msg) { g_err = msg; return code; }
 struct msim_handle_s {
     KParams kp;                 // layout + scalar parameters (args filled per run)
     int policy;
-    int aos;                    // 1: array-of-structures slab + msim::aos kernels (default); 0: MSIM_SLAB_LAYOUT=soa
     int n_sms;
     int warps_per_block[2];     // per rng mode (the Philox and replay kernels differ in register use)
     int blocks_per_sm[2];
     int regs[2];
+    int wide[2];                // 1: shared memory limits the handle to <= 4 CTAs per SM -> lean runs use the 64-register build
     size_t smem_bytes[2];
     unsigned long long* d_counter;
     double span;                // run_until - warmup
@@ -108,17 +108,6 @@ extern "C" int msim_create(const msim_tables_t* t, msim_handle_t* out) {
     msim_handle_s* h = new msim_handle_s();
     memset(&h->kp, 0, sizeof(h->kp));
     h->policy = t->policy;
-    {
-        // Slab layout, read per handle.  Default: array-of-structures (msim_kernel_aos.cu), +6..7 % on a B200
-        // (profiles/r01_slab_layout_probe.jsonl); MSIM_SLAB_LAYOUT=soa selects the structure-of-arrays build
-        // (msim_kernel.cu) that all earlier round-1 measurements were taken with.
-        const char* lay = getenv("MSIM_SLAB_LAYOUT");
-        h->aos = !(lay && strcmp(lay, "soa") == 0);
-        if (lay && strcmp(lay, "soa") != 0 && strcmp(lay, "aos") != 0) {
-            delete h;
-            return fail(MSIM_E_INVALID, "MSIM_SLAB_LAYOUT must be soa or aos");
-        }
-    }
     h->d_scratch = nullptr; h->scratch_bytes = 0;
     Lay& L = h->kp.lay;
     L.R = R; L.P = P; L.S = S;
@@ -130,58 +119,29 @@ extern "C" int msim_create(const msim_tables_t* t, msim_handle_t* out) {
     if (L.MP > 250 || L.MD > 250 || (L.NQ & (L.NQ - 1))) { delete h; return fail(MSIM_E_INVALID, "bad pool capacities"); }
     L.K = 11 * P + 4 * R + 3;
     const bool dbr = t->policy == MSIM_POLICY_DBR;
-    const bool prio = t->policy == MSIM_POLICY_MAX_PRIORITY || t->policy == MSIM_POLICY_EDD;
     const bool on_due = t->delivery_mode == MSIM_DELIVERY_ON_DUE;
 
     // ---- per-replication slab layout
     int off = 0;
     auto take = [&](int bytes, int align) { off = align_up(off, align); int o = off; off += bytes; return o; };
-    if (h->aos) {
-        // struct arrays first (resources at slab offset 0, msim_kernel_aos.cu), then what the whole warp reads
-        L.r_utf = take(R * kAosResStride, 4);
-        L.p_fg = take(P * kAosPrdStride, 4);
-        L.po_rel = take(L.MP * aos_po_stride(t->policy), 4);
-        L.do_arr = take(L.MD * kAosDoStride, 4);
-        L.do_prod = take(L.MD * kAosDoLinkStride, 2);
-        L.stage = take(kStageCap * 16, 16);
-        L.nq = take(L.NQ * 4, 4);
-        L.uq = take(L.UQ * 4, 4);
-        L.tm_time = take(L.NT * 4, 4);
-        L.tm_eid = take(L.NT * 4, 4);
-        L.tm_ev = take(L.NT * 4, 4);
-        L.rb = take(2 * 16 * 8, 8);
-        L.r_tpy = dbr ? take(R * 8, 8) : 0; L.r_start_d = dbr ? take(R * 8, 8) : 0; L.r_utf_d = dbr ? take(R * 8, 8) : 0;
-        L.r_qq = t->log_queues ? take(R * 4, 4) : 0; L.r_lastq = t->log_queues ? take(R * 4, 4) : 0;
-        L.po_tt = dbr ? take(L.MP * 4, 4) : 0; L.po_eid = dbr ? take(L.MP * 4, 4) : 0;
-        L.do_tt = on_due ? take(L.MD * 4, 4) : 0; L.do_eid = on_due ? take(L.MD * 4, 4) : 0;
-        L.r_flags = dbr ? take(R, 1) : 0; L.po_relpy = dbr ? take(L.MP, 1) : 0;
-    } else {
-        L.stage = take(kStageCap * 16, 16);
-        L.nq = take(L.NQ * 4, 4);
-        L.uq = take(L.UQ * 4, 4);
-        L.tm_time = take(L.NT * 4, 4);
-        L.tm_eid = take(L.NT * 4, 4);
-        L.tm_ev = take(L.NT * 4, 4);
-        L.rb = take(2 * 16 * 8, 8);                 // precomputed (x,u) pairs of streams B,C (philox.cuh kXuBuf)
-        L.r_tpy = dbr ? take(R * 8, 8) : 0; L.r_start_d = dbr ? take(R * 8, 8) : 0; L.r_utf_d = dbr ? take(R * 8, 8) : 0;
-        L.r_utf = take(R * 4, 4); L.r_tbf = take(R * 4, 4); L.r_setup = take(R * 4, 4); L.r_start = take(R * 4, 4);
-        L.r_busy = take(R * 4, 4);
-        L.r_qq = t->log_queues ? take(R * 4, 4) : 0; L.r_lastq = t->log_queues ? take(R * 4, 4) : 0;   // `queue` records only
-        L.p_fg = take(P * 4, 4); L.p_wip = take(P * 4, 4); L.p_fgc = take(P * 4, 4); L.p_dqty = take(P * 4, 4);
-        L.p_ddue = take(P * 4, 4);
-        L.po_rel = take(L.MP * 4, 4); L.po_qty = take(L.MP * 4, 4);
-        L.po_prio = prio ? take(L.MP * 4, 4) : 0;
-        L.po_tt = dbr ? take(L.MP * 4, 4) : 0; L.po_eid = dbr ? take(L.MP * 4, 4) : 0; L.po_ccr = dbr ? take(L.MP * 4, 4) : 0;
-        L.do_arr = take(L.MD * 4, 4); L.do_due = take(L.MD * 4, 4); L.do_qty = take(L.MD * 4, 4);
-        L.do_tt = on_due ? take(L.MD * 4, 4) : 0;  // delivery timers exist only in onDue mode
-        L.do_eid = on_due ? take(L.MD * 4, 4) : 0;
-        L.r_flags = dbr ? take(R, 1) : 0; L.po_relpy = dbr ? take(L.MP, 1) : 0;
-        L.r_cur = take(R, 1); L.r_tcur = take(R, 1);
-        L.r_inh = take(R, 1); L.r_int = take(R, 1); L.r_outh = take(R, 1); L.r_outt = take(R, 1);
-        L.p_obh = take(P, 1); L.p_obt = take(P, 1); L.p_fgqh = take(P, 1); L.p_fgqt = take(P, 1);
-        L.po_prod = take(L.MP, 1); L.po_done = take(L.MP, 1); L.po_next = take(L.MP, 1); L.po_loc = take(L.MP, 1);
-        L.do_prod = take(L.MD, 1); L.do_next = take(L.MD, 1);
-    }
+    // struct arrays first (resources at slab offset 0, msim_kernel.cu), then what the whole warp reads
+    L.r_utf = take(R * kAosResStride, 4);
+    L.p_fg = take(P * kAosPrdStride, 4);
+    L.po_rel = take(L.MP * aos_po_stride(t->policy), 4);
+    L.do_arr = take(L.MD * kAosDoStride, 4);
+    L.do_prod = take(L.MD * kAosDoLinkStride, 2);
+    L.stage = take(kStageCap * 16, 16);
+    L.nq = take(L.NQ * 4, 4);
+    L.uq = take(L.UQ * 4, 4);
+    L.tm_time = take(L.NT * 4, 4);
+    L.tm_eid = take(L.NT * 4, 4);
+    L.tm_ev = take(L.NT * 4, 4);
+    L.rb = take(2 * 16 * 8, 8);                    // precomputed (x,u) pairs of streams B,C (philox.cuh kXuBuf)
+    L.r_tpy = dbr ? take(R * 8, 8) : 0; L.r_start_d = dbr ? take(R * 8, 8) : 0; L.r_utf_d = dbr ? take(R * 8, 8) : 0;
+    L.r_qq = t->log_queues ? take(R * 4, 4) : 0; L.r_lastq = t->log_queues ? take(R * 4, 4) : 0;   // `queue` records only
+    L.po_tt = dbr ? take(L.MP * 4, 4) : 0; L.po_eid = dbr ? take(L.MP * 4, 4) : 0;
+    L.do_tt = on_due ? take(L.MD * 4, 4) : 0; L.do_eid = on_due ? take(L.MD * 4, 4) : 0;   // delivery timers: onDue only
+    L.r_flags = dbr ? take(R, 1) : 0; L.po_relpy = dbr ? take(L.MP, 1) : 0;
     L.scal = take((int)sizeof(Scal), 8);
     L.slab_bytes = align_up(off, 16);
 
@@ -267,19 +227,22 @@ extern "C" int msim_create(const msim_tables_t* t, msim_handle_t* out) {
     // warps per block: maximise resident replications (= warps) per SM.  Shared memory, the per-CTA copy of the
     // tables and the register file all bound it, so ask the occupancy calculator for every CTA width.
     const size_t smem_blk_max = prop.sharedMemPerBlockOptin;           // 227 KB
+    // MSIM_MAX_CTAS_PER_SM (diagnostic): caps the resident CTAs per SM, to measure throughput against occupancy
+    int cta_cap = 0;
+    if (const char* e = getenv("MSIM_MAX_CTAS_PER_SM")) cta_cap = atoi(e);
     for (int rng = 0; rng < 2; ++rng) {
         int best_w = 0, best_total = 0, best_blocks = 0;
         for (int w = 1; w <= 8; ++w) {
             size_t need = (size_t)w * L.slab_bytes;
             if (need > smem_blk_max) break;
             int nblk = 0, regs = 0;
-            int rc = h->aos ? aos::sim_kernel_attrs(h->policy, rng, need, &regs, w * 32, &nblk)
-                            : sim_kernel_attrs(h->policy, rng, need, &regs, w * 32, &nblk);
+            int rc = sim_kernel_attrs(h->policy, rng, false, need, &regs, w * 32, &nblk);
             if (rc != 0) {
                 delete h;
                 return fail(rc, rc == MSIM_E_UNSUPPORTED ? "policy not available in this build" : "kernel attribute query failed");
             }
             h->regs[rng] = regs;
+            if (cta_cap > 0 && nblk > cta_cap) nblk = cta_cap;
             int warps = nblk * w;
             if (warps > best_total || (warps == best_total && w > best_w)) { best_total = warps; best_w = w; best_blocks = nblk; }
         }
@@ -287,14 +250,25 @@ extern "C" int msim_create(const msim_tables_t* t, msim_handle_t* out) {
         h->warps_per_block[rng] = best_w;
         h->blocks_per_sm[rng] = best_blocks;
         h->smem_bytes[rng] = (size_t)best_w * L.slab_bytes;
+        // <= 4 CTAs per SM by shared memory: the 64-register build of the lean kernels keeps the same residency
+        h->wide[rng] = 0;
+        if (best_blocks <= 4) {
+            int nblk = 0, regs = 0;
+            if (sim_kernel_attrs(h->policy, rng, true, h->smem_bytes[rng], &regs, best_w * 32, &nblk) == 0 &&
+                (cta_cap > 0 && nblk > cta_cap ? cta_cap : nblk) >= best_blocks)
+                h->wide[rng] = 1;
+        }
     }
     if (cudaMalloc(&h->d_counter, 8) != cudaSuccess) {
         delete h;
         return fail(MSIM_E_NOMEM, "cudaMalloc failed");
     }
     kp.work_counter = h->d_counter;
-    CU(cudaEventCreate(&h->ev0));
-    CU(cudaEventCreate(&h->ev1));
+    h->ev0 = nullptr; h->ev1 = nullptr;
+    if (cudaEventCreate(&h->ev0) != cudaSuccess || cudaEventCreate(&h->ev1) != cudaSuccess) {
+        msim_destroy(h);
+        return fail(MSIM_E_CUDA, "cudaEventCreate failed");
+    }
     *out = h;
     return 0;
 }
@@ -303,8 +277,8 @@ extern "C" int msim_destroy(msim_handle_t h) {
     if (!h) return 0;
     cudaFree(h->d_counter);
     if (h->d_scratch) cudaFree(h->d_scratch);
-    cudaEventDestroy(h->ev0);
-    cudaEventDestroy(h->ev1);
+    if (h->ev0) cudaEventDestroy(h->ev0);
+    if (h->ev1) cudaEventDestroy(h->ev1);
     delete h;
     return 0;
 }
@@ -346,8 +320,7 @@ extern "C" int msim_run(msim_handle_t h, const msim_run_args_t* a) {
     long long blocks_needed = (a->n_reps + wpb - 1) / wpb;
     long long grid = (long long)h->n_sms * h->blocks_per_sm[rng];
     if (grid > blocks_needed) grid = blocks_needed;
-    int rc = h->aos ? aos::launch_sim(kp, h->policy, rng, (int)grid, wpb * 32, h->smem_bytes[rng], st)
-                    : launch_sim(kp, h->policy, rng, (int)grid, wpb * 32, h->smem_bytes[rng], st);
+    int rc = launch_sim(kp, h->policy, rng, h->wide[rng] != 0, (int)grid, wpb * 32, h->smem_bytes[rng], st);
     if (rc != 0) return fail(rc, "simulation kernel launch failed (grid/block/shared-memory configuration)");
     return 0;
 }
@@ -385,6 +358,9 @@ extern "C" int msim_run_host(msim_handle_t h, const msim_host_args_t* a) {
         la = a->tape_A_off[n]; lb = a->tape_B_off[n]; lc = a->tape_C_off[n]; ld = a->tape_D_off[n];
     }
     const bool logs = a->log && a->n_log_reps > 0 && a->log_cap > 0;
+    const bool logs_dev = a->log_dev && a->n_log_reps_dev > 0 && a->log_cap_dev > 0;
+    if (logs && logs_dev) return fail(MSIM_E_INVALID, "host log rings and device log rings are mutually exclusive");
+    if (logs_dev && !a->log_count_dev) return fail(MSIM_E_INVALID, "device log rings need log_count_dev");
     const int64_t nlog = logs ? (a->n_log_reps < n ? a->n_log_reps : n) : 0;
     // carve one scratch allocation
     size_t off = 0;
@@ -431,12 +407,19 @@ extern "C" int msim_run_host(msim_handle_t h, const msim_host_args_t* a) {
         r.log = (msim_record_t*)(base + o_log); r.log_count = (uint32_t*)(base + o_lc);
         r.log_cap = a->log_cap; r.n_log_reps = nlog;
         CU(cudaMemsetAsync(base + o_lc, 0, (size_t)nlog * 4, st));
+    } else if (logs_dev) {                       // records stream into the caller's HBM rings and stay there
+        r.log = a->log_dev; r.log_count = a->log_count_dev;
+        r.log_cap = a->log_cap_dev; r.n_log_reps = a->n_log_reps_dev < n ? a->n_log_reps_dev : n;
     }
     r.stream = st;
     CU(cudaEventRecord(h->ev0, st));
     int rc = msim_run(h, &r);
     if (rc != 0) return rc;
     CU(cudaEventRecord(h->ev1, st));
+    if (a->stats_dev) {
+        rc = msim_reduce_metrics(h, r.acc_sum, r.acc_cnt, r.status, n, a->stats_dev, st);
+        if (rc != 0) return rc;
+    }
     if (a->acc_sum) CU(cudaMemcpyAsync(a->acc_sum, r.acc_sum, (size_t)n * L.K * 8, cudaMemcpyDeviceToHost, st));
     if (a->acc_cnt) CU(cudaMemcpyAsync(a->acc_cnt, r.acc_cnt, (size_t)n * L.K * 4, cudaMemcpyDeviceToHost, st));
     if (a->n_events) CU(cudaMemcpyAsync(a->n_events, r.n_events, (size_t)n * 8, cudaMemcpyDeviceToHost, st));

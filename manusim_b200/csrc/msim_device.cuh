@@ -1,4 +1,4 @@
-// Shared declarations between the simulation kernel (msim_kernel.cu) and the host C ABI (msim_api.cu).
+// Shared declarations between the kernels (msim_kernel.cu, msim_reduce.cu) and the host C ABI (msim_api.cu).
 #pragma once
 #include <stdint.h>
 #include "../../include/msim.h"
@@ -49,31 +49,21 @@ struct Scal {
     uint8_t drain_wait;     // _update_constraint_buffer blocked on resource_finished[CCR].get()
     uint8_t fin_n;          // items in resource_finished[CCR]
     uint8_t fin[5];
-#if defined(MSIM_X_DUECACHE) && MSIM_X_DUECACHE
-    // experiment (msim_kernel_aos.cu): earliest pending onDue delivery timer, kept up to date by lane 0 so that the
-    // per-pop scan of all demand-order timers only runs after one of them fired
-    uint32_t due_t, due_e, due_slot, due_cnt;   // float bits of the earliest time, its smallest eid, calendar slot, ties
-    uint32_t due_dirty;
-#endif
-#if defined(MSIM_X_ROPECACHE) && MSIM_X_ROPECACHE
-    uint32_t rope_t, rope_e, rope_slot, rope_cnt, rope_dirty;   // same for the DBR process_order delay timers
-#endif
 };
 
 // byte offsets of every per-replication array inside the warp's shared-memory slab and of every table
 // inside the scenario table blob (KParams::tblob).  Computed once per handle on the host.
 struct Lay {
     int32_t R, P, S, NT, MP, MD, NQ, UQ, K;
-    // per-replication slab
+    // per-replication slab.  Entity state is array-of-structures (strides below): r_utf (= 0), p_fg, po_rel, do_arr
+    // and do_prod hold the start of the resource / product / production-order / demand-order (three floats; two link
+    // bytes) struct arrays.  What the whole warp reads is structure-of-arrays, one slot per lane.
     int32_t stage, nq, uq, tm_time, tm_eid, tm_ev, rb;
-    int32_t r_utf, r_tbf, r_setup, r_start, r_busy, r_qq, r_lastq;
-    int32_t p_fg, p_wip, p_fgc, p_dqty, p_ddue;
-    int32_t po_rel, po_qty, po_prio, po_tt, po_eid, po_ccr;
-    int32_t do_arr, do_due, do_qty, do_tt, do_eid;
+    int32_t r_utf, p_fg, po_rel, do_arr, do_prod;
+    int32_t r_qq, r_lastq;                                   // `queue` records only (log_queues)
+    int32_t po_tt, po_eid;                                   // DBR: process_order delay timers
+    int32_t do_tt, do_eid;                                   // onDue: delivery timers
     int32_t r_tpy, r_start_d, r_utf_d, r_flags, po_relpy;   // DBR: python-typed clock excursions (Appendix B.2)
-    int32_t r_cur, r_tcur, r_inh, r_int, r_outh, r_outt;
-    int32_t p_obh, p_obt, p_fgqh, p_fgqt;
-    int32_t po_prod, po_done, po_next, po_loc, do_prod, do_next;
     int32_t scal, slab_bytes;
     // scenario tables (offsets into KParams::tblob)
     int32_t t_route_start, t_step_res, t_step_dist, t_setup, t_tbf, t_ttr, t_freq, t_qty, t_due, t_shipbuf, t_ccrpt,
@@ -94,19 +84,15 @@ struct KParams {
     msim_run_args_t a;             // device pointers
 };
 
-// array-of-structures slab of the experimental kernel twin (msim_kernel_aos.cu): struct strides in bytes.  In that
-// layout Lay::r_utf (= 0), p_fg, po_rel, do_arr and do_prod hold the start of the resource / product / production-
-// order / demand-order (floats; link bytes) struct arrays and the other per-field offsets of those entities are unused.
+// struct strides of the entity arrays inside the slab, in bytes (field offsets: msim_kernel.cu)
 constexpr int kAosResStride = 28, kAosPrdStride = 24, kAosDoStride = 12, kAosDoLinkStride = 2;
 __host__ __device__ constexpr int aos_po_stride(int policy) { return policy == MSIM_POLICY_FIFO ? 12 : 16; }   // + prio (PRIO/EDD) or ccr (DBR)
-namespace aos {
-int launch_sim(const KParams& p, int policy, int rng_mode, int grid, int block, size_t smem, void* stream);
-int sim_kernel_attrs(int policy, int rng_mode, size_t smem, int* regs, int block, int* blocks_per_sm);
-}
 
-// launchers implemented in msim_kernel.cu
-int launch_sim(const KParams& p, int policy, int rng_mode, int grid, int block, size_t smem, void* stream);
-int sim_kernel_attrs(int policy, int rng_mode, size_t smem, int* regs, int block, int* blocks_per_sm);
+// launchers implemented in msim_kernel.cu.  `wide`: the 64-register build of the lean kernels (handles that shared
+// memory limits to <= 4 CTAs per SM); the launcher picks the lean kernel itself when the run uses no option.
+int launch_sim(const KParams& p, int policy, int rng_mode, bool wide, int grid, int block, size_t smem, void* stream);
+int sim_kernel_attrs(int policy, int rng_mode, bool wide, size_t smem, int* regs, int block, int* blocks_per_sm);
+// launchers implemented in msim_reduce.cu
 int launch_reduce(const double* acc_sum, const uint32_t* acc_cnt, const int32_t* status, int64_t n_reps, int K, int P,
                   int R, double span, double* out, void* stream);
 int launch_reduce_variables(const double* acc_sum, const uint32_t* acc_cnt, const int32_t* status, int64_t n_reps, int K,

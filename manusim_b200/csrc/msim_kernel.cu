@@ -1,11 +1,11 @@
 // msim_kernel.cu -- the batched factory-replication kernel for B200 (sm_100a).
 //
 // One WARP owns one replication.  Everything the reference keeps in SimPy objects lives in a per-warp slab of
-// shared memory (layout: msim_device.cuh `Lay`):
+// shared memory (layout: msim_device.cuh `Lay`, sized by msim_api.cu):
 //   * event calendar  : one (time f32, eid) slot per static process that can sleep on a Timeout
 //                       (R machines, P demand generators, warm-up, DBR tick) + per-order slots for onDue
-//                       delivery timers; the next event is picked by a warp-wide shuffle min-reduction over
-//                       (time, eid) -- SimPy's heap order (time, priority, eid) restricted to Timeouts;
+//                       delivery timers / DBR rope delays; the next event is picked by a warp-wide min-reduction
+//                       over (time, eid) -- SimPy's heap order (time, priority, eid) restricted to Timeouts;
 //   * zero-delay events: SimPy schedules every put/get/request completion as a heap event at `now`.  Because
 //                       eids only grow, those behave as two FIFOs (URGENT = process Initialize, NORMAL = the
 //                       rest).  Lane 0 drains them literally, one micro-event at a
@@ -18,21 +18,81 @@
 //                       the replication's HBM ring; the same flush folds the records into per-ring
 //                       (sum f64, count) accumulators (warm-up filtering happens at emission, as in the
 //                       reference).
-// Scheduling rules (FIFO / max-priority / DBR / EDD) are template parameters, so is the variate source
-// (Philox4x32-10 keyed by replication/stream/draw index, or replay of host-recorded tapes).  Scenario tables
-// (routes, distributions) travel in the kernel parameters and are read with LDC; they use no shared memory.
-// Lane 0's loop state is split: what every micro-event touches stays in registers, the rest lives in the slab
-// (`Scal`), which keeps the kernel at 48 registers per thread with few spills.
+// Entity state that only lane 0 touches is an array of small structs per entity kind -- resource 28 B (at slab
+// offset 0), product 24 B, production order 12 / 16 B, demand order 12 B + 2 link bytes -- so a handler pays one
+// multiply-add per ENTITY and reaches its 3-8 fields with immediate offsets; what the whole warp reads (calendar,
+// per-order timers, event FIFOs, log staging, variate buffer) is structure-of-arrays, one slot per lane.
+// Scheduling rules (FIFO / max-priority / DBR / EDD) are template parameters, so are the variate source
+// (Philox4x32-10 keyed by replication/stream/draw index, or replay of host-recorded tapes) and the option flags
+// (queue records, tape recording).  Scenario tables (routes, distributions) travel in the kernel parameters and are
+// read with LDC; they use no shared memory.  Lane 0's loop state is split: what every micro-event touches stays in
+// registers, the rest lives in the slab (`Scal`).
+// The kernel is instruction-fetch bound (profiles/README.md): code size and the density of the hot path decide its
+// speed, which is why cold paths are out of line and options are compile-time.
 //
 // Reference anchors are given next to each handler as file:line of /root/reference/src/manusim/factory_sim.py.
 #include <cuda_runtime.h>
 #include <math_constants.h>
+#include <stdlib.h>
 #include "msim_device.cuh"
 #include "philox.cuh"
 
+// ---- build switches (tools/ab_probe.py builds -D variants next to libmsim.so and times them on identical
+// trajectories; every variant is first checked bit for bit on the CPU-fiber emulation).  Measured on a B200 in round 2
+// (profiles/r02_ab_probe.jsonl) and folded in: the shared out-of-line "push the successor and leave" exit of the
+// chained handlers (+10 %), the OPTS = 0 kernels (+15..23 %); measured and dropped: per-ring-group log flush (-5 %),
+// cached earliest onDue / rope timer (-5 % / 0: the extra code costs more than the scan it saves), counting calendar
+// pops at the end (0).  (Byte-identical SASS, hence never timed: __builtin_expect on the error / option branches, an
+// equality chain on the hottest micro-events in front of the handler switch.)
+#ifndef MSIM_X_F32CELL     // 1 = NEGATIVE CONTROL for tests/test_emu_kernel.py: order the DBR calendar by float32 time alone
+#define MSIM_X_F32CELL 0   //     (the round-1 behaviour; golden dbr_f64_order must fail with it)
+#endif
+// Option flags as a template parameter: OPTS bit 0 = the scenario may log `queue` records (config log_queues), bit 1 =
+// the run may record variate tapes (rec_cap > 0).  OPTS = 3 is the general kernel; OPTS = 0 drops both branches from
+// every handler (-8 % code) and is what a run that uses neither option launches.
+// MINB = __launch_bounds__(256, MINB): 5 -> 48 registers (40 resident warps when shared memory allows 5 CTAs per SM);
+// 4 -> 64 registers and no spills, launched when shared memory limits the handle to 4 CTAs per SM anyway (onDue pools:
+// +12 % there, -26 % where it would cost a CTA).
+#define LOGQ (((OPTS) & 1) && p.log_queues)
+#define RECORDING (((OPTS) & 2) && p.a.rec_cap > 0)
+#define NOT_RECORDING (!((OPTS) & 2) || p.a.rec_cap == 0)
+#define PUSH_AND_LEAVE(ev) { tail_ev = (ev); goto L_TAIL_PUSH; }
 namespace msim {
 
 #define FULLMASK 0xFFFFFFFFu
+
+// struct layouts inside the slab (byte offsets; msim_api.cu sizes the slab with the same strides, msim_device.cuh)
+enum { kRes_utf = 0, kRes_tbf = 4, kRes_setup = 8, kRes_start = 12, kRes_busy = 16, kRes_cur = 20, kRes_tcur = 21,
+       kRes_inh = 22, kRes_int = 23, kRes_outh = 24, kRes_outt = 25 };
+enum { kPrd_fg = 0, kPrd_wip = 4, kPrd_fgc = 8, kPrd_dqty = 12, kPrd_ddue = 16, kPrd_obh = 20, kPrd_obt = 21,
+       kPrd_fgqh = 22, kPrd_fgqt = 23 };
+enum { kPo_rel = 0, kPo_qty = 4, kPo_prod = 8, kPo_done = 9, kPo_next = 10, kPo_loc = 11, kPo_prio = 12, kPo_ccr = 12 };
+// demand orders are two struct arrays (three floats; two link bytes): one 16-byte struct would waste 2 bytes per
+// order, i.e. a CTA's worth of occupancy at the pool sizes the 20-resource job shop needs
+enum { kDo_arr = 0, kDo_due = 4, kDo_qty = 8, kDo_prod = 0, kDo_next = 1 };
+static_assert(kAosResStride >= 26 && kAosPrdStride >= 24 && kAosDoStride == 12 && kAosDoLinkStride == 2,
+              "struct strides (msim_device.cuh)");
+#define kDoBase_arr p.lay.do_arr
+#define kDoBase_due p.lay.do_arr
+#define kDoBase_qty p.lay.do_arr
+#define kDoBase_prod p.lay.do_prod
+#define kDoBase_next p.lay.do_prod
+#define kDoStr_arr kAosDoStride
+#define kDoStr_due kAosDoStride
+#define kDoStr_qty kAosDoStride
+#define kDoStr_prod kAosDoLinkStride
+#define kDoStr_next kAosDoLinkStride
+
+// entity fields: resource structs start at slab offset 0; the product / order struct arrays start where the layout
+// table keeps the first field of the SoA slab (p_fg, po_rel, do_arr; do_prod for the demand-order link bytes)
+#define ARR(T, field) (reinterpret_cast<T*>(sb + p.lay.field))
+#define TAB(T, field) (reinterpret_cast<const T*>(p.tblob + p.lay.field))
+#define RES(T, f, i) (*reinterpret_cast<T*>(sb + (uint32_t)(i) * kAosResStride + kRes_##f))
+#define PRD(T, f, i) (*reinterpret_cast<T*>(sb + p.lay.p_fg + (uint32_t)(i) * kAosPrdStride + kPrd_##f))
+#define PORD(T, f, i) (*reinterpret_cast<T*>(sb + p.lay.po_rel + (uint32_t)(i) * kPoStride + kPo_##f))
+#define DORD(T, f, i) (*reinterpret_cast<T*>(sb + kDoBase_##f + (uint32_t)(i) * kDoStr_##f + kDo_##f))
+#define PO_NEXT (sb + p.lay.po_rel + kPo_next)
+#define DO_NEXT (sb + p.lay.do_prod + kDo_next)
 
 // Launch syntax and the dynamic shared-memory declaration go through two macros so that the host-side SIMT emulator
 // under tests/emu (test infrastructure: runs THIS source on CPU fibers for sanitizer and parity checks, never part of
@@ -95,6 +155,7 @@ __device__ __forceinline__ double pyround6(double x) {
 // demand triplets) and as the fallback of the inlined fast paths (buffer miss, Marsaglia-Tsang squeeze failure,
 // shape < 1, batches of more than one sample, tape recording).  Bumps the stream's draw index itself.
 // count < 0: scalar draw (DistributionGenerator.random_number, clamped at 0); count >= 0: batch sum.
+template <int OPTS>
 __device__ __noinline__ double philox_draw_slow(const KParams& p, Scal* sc, const float2* rb, long long rep, int stream,
                                                 const DDist* d, int count) {
     const uint32_t idx = sc->draw[stream]++;
@@ -121,14 +182,14 @@ __device__ __noinline__ double philox_draw_slow(const KParams& p, Scal* sc, cons
         }
         out = (double)v;
     }
-    if (p.a.rec_cap > 0 && (long long)idx < p.a.rec_cap) {
+    if (RECORDING && (long long)idx < p.a.rec_cap) {
         if (stream == 2) p.a.rec_C[rep * p.a.rec_cap + idx] = out;
         else (stream == 0 ? p.a.rec_A : (stream == 1 ? p.a.rec_B : p.a.rec_D))[rep * p.a.rec_cap + idx] = (float)out;
     }
     return out;
 }
 
-template <int POLICY, int RNG>
+template <int POLICY, int RNG, int OPTS>
 struct Sim {
     const KParams& p;
     unsigned char* sb;        // this warp's slab
@@ -155,8 +216,7 @@ struct Sim {
           same_left(sc_->x_same_left), pending(sc_->x_pending), rb_need(sc_->x_rb_need), now_py(sc_->x_now_py),
           sel_req(sc_->x_sel_req), status(sc_->x_status), now_d(sc_->x_now_d) {}
 
-#define ARR(T, field) (reinterpret_cast<T*>(sb + p.lay.field))
-#define TAB(T, field) (reinterpret_cast<const T*>(p.tblob + p.lay.field))
+    static constexpr int kPoStride = aos_po_stride(POLICY), kDoStride = kAosDoLinkStride;
 
     __device__ __forceinline__ int ringP(int m, int prod) const { return m * p.lay.P + prod; }
     __device__ __forceinline__ int ringR(int m, int r) const { return 11 * p.lay.P + m * p.lay.R + r; }
@@ -197,7 +257,7 @@ struct Sim {
         const uint32_t idx = sc->draw[stream];
         const uint32_t off = idx - sc->rb_base[stream];
         if (off >= (uint32_t)kXuBuf - kXuRefillAt) rb_need |= 1u << stream;
-        if (off >= (uint32_t)kXuBuf || p.a.rec_cap > 0) return false;
+        if (off >= (uint32_t)kXuBuf || RECORDING) return false;
         const float2 xu = ARR(float2, rb)[(stream - 1) * kXuBuf + off];
         if (d.kind == MSIM_DIST_NORMAL) {
             v = d.d0 + d.d1 * xu.x;
@@ -216,7 +276,7 @@ struct Sim {
         if (RNG == MSIM_RNG_REPLAY) return draw_scalar(stream, d);
         float v;
         if (fast_sample(stream, d, v)) return v > 0.0f ? v : 0.0f;
-        return (float)philox_draw_slow(p, sc, ARR(float2, rb), rep, stream, &d, -1);
+        return (float)philox_draw_slow<OPTS>(p, sc, ARR(float2, rb), rep, stream, &d, -1);
     }
     __device__ __forceinline__ float draw_scalar(int stream, const DDist& d) {
         if (RNG == MSIM_RNG_REPLAY) {
@@ -224,11 +284,11 @@ struct Sim {
             if (idx >= sc->tlen[stream]) { fail(MSIM_ST_TAPE_EXHAUSTED); return 0.0f; }
             return __ldg(reinterpret_cast<const float*>(sc->tbase[stream]) + idx);
         }
-        if (d.kind == MSIM_DIST_CONSTANT && p.a.rec_cap == 0) {   // max(0, np.float32(params[0])): no generator involved
+        if (d.kind == MSIM_DIST_CONSTANT && NOT_RECORDING) {   // max(0, np.float32(params[0])): no generator involved
             sc->draw[stream]++;
             return d.d0 > 0.0f ? d.d0 : 0.0f;
         }
-        return (float)philox_draw_slow(p, sc, ARR(float2, rb), rep, stream, &d, -1);
+        return (float)philox_draw_slow<OPTS>(p, sc, ARR(float2, rb), rep, stream, &d, -1);
     }
     __device__ __forceinline__ double draw_batch(const DDist& d, int count) {
         if (RNG == MSIM_RNG_REPLAY) {
@@ -238,7 +298,7 @@ struct Sim {
         }
         float v;
         if (count == 1 && fast_sample(2, d, v)) return (double)((d.kind == MSIM_DIST_NORMAL && !(v > 0.0f)) ? 0.0f : v);
-        return philox_draw_slow(p, sc, ARR(float2, rb), rep, 2, &d, count < 0 ? 0 : count);
+        return philox_draw_slow<OPTS>(p, sc, ARR(float2, rb), rep, 2, &d, count < 0 ? 0 : count);
     }
 
     // ------------------------------------------------------------------ records (Logger.log, logs.py:44-66)
@@ -249,15 +309,15 @@ struct Sim {
     }
     // _log_inventory_metrics, factory_sim.py:551-601 (caller checked warm)
     __device__ __forceinline__ void inventory(int prod, bool with_wip, bool with_fg) {
-        float w = ARR(float, p_wip)[prod];
-        float f = ARR(float, p_fg)[prod];
+        float w = PRD(float, wip, prod);
+        float f = PRD(float, fg, prod);
         if (with_wip) {
             emit(ringP(PM_WIP, prod), now, w);
             emit(ringG(GM_WIP), now, sc->tot_wip);
         }
         if (with_fg) {
-            float old = ARR(float, p_fgc)[prod];
-            ARR(float, p_fgc)[prod] = f;
+            float old = PRD(float, fgc, prod);
+            PRD(float, fgc, prod) = f;
             sc->fgc_sum = __fadd_rn(sc->fgc_sum, __fsub_rn(f, old));
             emit(ringP(PM_FG, prod), now, f);
             emit(ringG(GM_FG), now, sc->fgc_sum);
@@ -267,8 +327,8 @@ struct Sim {
     }
     // _log_delivery_performance + _log_lead_time, factory_sim.py:606-654
     __device__ __forceinline__ void delivery_records(int d, int prod, bool delivered) {
-        float q = ARR(float, do_qty)[d];
-        float due = ARR(float, do_due)[d];
+        float q = DORD(float, qty, d);
+        float due = DORD(float, due, d);
         if (!delivered || now == 0.0f) {          // `if not delivered` (also true for delivered == 0, quirk E6)
             emit(ringP(PM_LOST, prod), now, q);
         } else if (now <= due) {
@@ -278,7 +338,7 @@ struct Sim {
             emit(ringP(PM_LATE, prod), now, q);
             emit(ringP(PM_TARDY, prod), now, __fsub_rn(now, due));
         }
-        emit(ringP(PM_LEAD, prod), now, __fsub_rn(now, ARR(float, do_arr)[d]));
+        emit(ringP(PM_LEAD, prod), now, __fsub_rn(now, DORD(float, arr, d)));
     }
     // resource `queue` records, factory_sim.py:227-242 / 343-358
     __device__ __forceinline__ void queue_log_add(int r, float q) {
@@ -298,70 +358,71 @@ struct Sim {
     __device__ __forceinline__ uint32_t alloc_po() {
         uint32_t i = sc->po_free;
         if (i == kNone) { fail(MSIM_ST_PO_POOL_OVERFLOW); return 0; }
-        sc->po_free = ARR(uint8_t, po_next)[i];
+        sc->po_free = PORD(uint8_t, next, i);
         if (DBR) ARR(float, po_tt)[i] = CUDART_INF_F;
         return i;
     }
     __device__ __forceinline__ void free_po(uint32_t i) {
-        ARR(uint8_t, po_next)[i] = sc->po_free;
-        ARR(uint8_t, po_loc)[i] = LOC_NONE;
+        PORD(uint8_t, next, i) = sc->po_free;
+        PORD(uint8_t, loc, i) = LOC_NONE;
         sc->po_free = (uint8_t)i;
     }
     __device__ __forceinline__ uint32_t alloc_do() {
         uint32_t i = sc->do_free;
         if (i == kNone) { fail(MSIM_ST_DO_POOL_OVERFLOW); return 0; }
-        sc->do_free = ARR(uint8_t, do_next)[i];
+        sc->do_free = DORD(uint8_t, next, i);
         return i;
     }
     __device__ __forceinline__ void free_do(uint32_t i) {
-        ARR(uint8_t, do_next)[i] = sc->do_free;
+        DORD(uint8_t, next, i) = sc->do_free;
         sc->do_free = (uint8_t)i;
     }
-    // generic singly linked FIFO through a `next` byte array
-    __device__ __forceinline__ void list_append(uint8_t* head, uint8_t* tail, uint8_t* next, uint32_t i) {
-        next[i] = kNone;
+    // singly linked FIFOs through the `next` byte of the order pools; `next0` addresses entry 0's byte and STRIDE is
+    // the distance to the next entry's (1 in the structure-of-arrays slab, the struct size in the AoS slab)
+    template <int STRIDE>
+    __device__ __forceinline__ void list_append(uint8_t* head, uint8_t* tail, uint8_t* next0, uint32_t i) {
+        next0[i * STRIDE] = kNone;
         uint32_t t = *tail;
-        if (t == kNone) *head = (uint8_t)i; else next[t] = (uint8_t)i;
+        if (t == kNone) *head = (uint8_t)i; else next0[t * STRIDE] = (uint8_t)i;
         *tail = (uint8_t)i;
     }
-    __device__ __forceinline__ uint32_t list_pop(uint8_t* head, uint8_t* tail, const uint8_t* next) {
+    template <int STRIDE>
+    __device__ __forceinline__ uint32_t list_pop(uint8_t* head, uint8_t* tail, const uint8_t* next0) {
         uint32_t h = *head;
-        uint32_t n = next[h];
+        uint32_t n = next0[h * STRIDE];
         *head = (uint8_t)n;
         if (n == kNone) *tail = kNone;
         return h;
     }
-
     // Container._trigger_get on finished_goods[prod]: serve blocked getters from the head, stop at the first
     // one that cannot be satisfied (SimPy Container._do_get returns None => head-of-line blocking)
     __device__ __forceinline__ void serve_fg(int prod) {
-        uint32_t h = ARR(uint8_t, p_fgqh)[prod];
+        uint32_t h = PRD(uint8_t, fgqh, prod);
         if (h == kNone) return;
-        float lvl = ARR(float, p_fg)[prod];
-        const uint8_t* nx = ARR(uint8_t, do_next);
+        float lvl = PRD(float, fg, prod);
         while (h != kNone) {
-            float q = ARR(float, do_qty)[h];
+            float q = DORD(float, qty, h);
             if (!(lvl >= q)) break;
             lvl = __fsub_rn(lvl, q);
             pushN(EV(OP_SHIP_GOT, prod, h));
-            h = nx[h];
+            h = DORD(uint8_t, next, h);
         }
-        ARR(float, p_fg)[prod] = lvl;
-        ARR(uint8_t, p_fgqh)[prod] = (uint8_t)h;
-        if (h == kNone) ARR(uint8_t, p_fgqt)[prod] = kNone;
+        PRD(float, fg, prod) = lvl;
+        PRD(uint8_t, fgqh, prod) = (uint8_t)h;
+        if (h == kNone) PRD(uint8_t, fgqt, prod) = kNone;
     }
     // finished_goods[prod].get(quantity) issued by a delivery process (ContainerGet.__init__)
     __device__ __forceinline__ void fg_get(int d, int prod) {
-        if (!(ARR(float, do_qty)[d] > 0.0f)) { fail(MSIM_ST_AMOUNT_NONPOSITIVE); return; }
-        list_append(ARR(uint8_t, p_fgqh) + prod, ARR(uint8_t, p_fgqt) + prod, ARR(uint8_t, do_next), d);
+        if (!(DORD(float, qty, d) > 0.0f)) { fail(MSIM_ST_AMOUNT_NONPOSITIVE); return; }
+        list_append<kDoStride>(&PRD(uint8_t, fgqh, prod), &PRD(uint8_t, fgqt, prod), DO_NEXT, d);
         serve_fg(prod);
     }
     // FilterStore._trigger_get on resource_input[r] when a put event is processed
     __device__ __forceinline__ void serve_mach(int r) {
         if ((sc->mach_wait >> r) & 1u) {
-            if (ARR(uint8_t, r_inh)[r] != kNone) {
-                uint32_t po = list_pop(ARR(uint8_t, r_inh) + r, ARR(uint8_t, r_int) + r, ARR(uint8_t, po_next));
-                ARR(uint8_t, po_loc)[po] = LOC_NONE;
+            if (RES(uint8_t, inh, r) != kNone) {
+                uint32_t po = list_pop<kPoStride>(&RES(uint8_t, inh, r), &RES(uint8_t, int, r), PO_NEXT);
+                PORD(uint8_t, loc, po) = LOC_NONE;
                 sc->mach_wait &= ~(1u << r);
                 pushN(EV(OP_MACH_GOT, r, po));
             }
@@ -369,9 +430,9 @@ struct Sim {
     }
     // _transportation loop top: resource_output[r].get()   factory_sim.py:298-302
     __device__ __forceinline__ void trans_get(int r) {
-        if (ARR(uint8_t, r_outh)[r] != kNone) {
-            uint32_t po = list_pop(ARR(uint8_t, r_outh) + r, ARR(uint8_t, r_outt) + r, ARR(uint8_t, po_next));
-            ARR(uint8_t, po_loc)[po] = LOC_NONE;
+        if (RES(uint8_t, outh, r) != kNone) {
+            uint32_t po = list_pop<kPoStride>(&RES(uint8_t, outh, r), &RES(uint8_t, outt, r), PO_NEXT);
+            PORD(uint8_t, loc, po) = LOC_NONE;
             pushN(EV(OP_TRANS_GOT, r, po));
         } else {
             sc->trans_wait |= 1u << r;
@@ -380,7 +441,7 @@ struct Sim {
     // scheduler loop top: inbound_demand_orders.get()      factory_sim.py:182
     __device__ __forceinline__ void sched_get() {
         if (sc->inb_head != kNone) {
-            uint32_t d = list_pop(&sc->inb_head, &sc->inb_tail, ARR(uint8_t, do_next));
+            uint32_t d = list_pop<kDoStride>(&sc->inb_head, &sc->inb_tail, DO_NEXT);
             pushN(EV(OP_SCHED_GOT, 0, d));
         } else {
             sc->sched_wait = 1;
@@ -388,8 +449,8 @@ struct Sim {
     }
     // _delivery_orders loop top: outbound[prod].get()       factory_sim.py:469-471
     __device__ __forceinline__ void deliv_get(int prod) {
-        if (ARR(uint8_t, p_obh)[prod] != kNone) {
-            uint32_t d = list_pop(ARR(uint8_t, p_obh) + prod, ARR(uint8_t, p_obt) + prod, ARR(uint8_t, do_next));
+        if (PRD(uint8_t, obh, prod) != kNone) {
+            uint32_t d = list_pop<kDoStride>(&PRD(uint8_t, obh, prod), &PRD(uint8_t, obt, prod), DO_NEXT);
             pushN(EV(OP_DELIV_GOT, prod, d));
         } else {
             sc->deliv_wait |= 1u << prod;
@@ -400,55 +461,52 @@ struct Sim {
         float gap = draw_scalar(0, TAB(DDist, t_freq)[prod]);
         float q = rintf(draw_scalar(0, TAB(DDist, t_qty)[prod]));     // round(x, 0): ties to even
         float due = draw_scalar(0, TAB(DDist, t_due)[prod]);
-        ARR(float, p_dqty)[prod] = q;
-        ARR(float, p_ddue)[prod] = due;
+        PRD(float, dqty, prod) = q;
+        PRD(float, ddue, prod) = due;
         timer(p.lay.R + prod, __fadd_rn(now, gap), EV(OP_TO_DEMAND, prod, 0));
     }
     // order_selection: policy is a compile-time device function
     // returns kNone unless `chain` is set and an order was picked: then the caller runs MACH_GOT itself
     __device__ __forceinline__ uint32_t mach_select(int r, bool chain = false) {
-        uint32_t h = ARR(uint8_t, r_inh)[r];
+        uint32_t h = RES(uint8_t, inh, r);
         if (h == kNone) { sc->mach_wait |= 1u << r; return kNone; }   // plain get() on an empty queue
         uint32_t pick = h;
         if (DBR) {
             // buffer-penetration dispatch (toc_dbr/simulation.py:291-328) needs a scan of every in-flight order:
             // a single queued order is trivially the minimum, otherwise the whole warp computes the priorities
-            if (ARR(uint8_t, po_next)[h] != kNone) { sel_req = (uint32_t)r + 1u; attn |= A_SELECT; return kNone; }
-            list_pop(ARR(uint8_t, r_inh) + r, ARR(uint8_t, r_int) + r, ARR(uint8_t, po_next));
+            if (PORD(uint8_t, next, h) != kNone) { sel_req = (uint32_t)r + 1u; attn |= A_SELECT; return kNone; }
+            list_pop<kPoStride>(&RES(uint8_t, inh, r), &RES(uint8_t, int, r), PO_NEXT);
         } else if (PRIO) {
             // max(orders, key=priority): first maximum in queue order (simple_scheduler/simulation.py:36)
-            const uint8_t* nx = ARR(uint8_t, po_next);
-            const float* pr = ARR(float, po_prio);
-            float best = pr[h];
+            float best = PORD(float, prio, h);
             uint32_t prev = kNone, pick_prev = kNone;
-            for (uint32_t i = h; i != kNone; prev = i, i = nx[i]) {
-                if (pr[i] > best) { best = pr[i]; pick = i; pick_prev = prev; }
+            for (uint32_t i = h; i != kNone; prev = i, i = PORD(uint8_t, next, i)) {
+                if (PORD(float, prio, i) > best) { best = PORD(float, prio, i); pick = i; pick_prev = prev; }
             }
             if (pick != h) {      // unlink from the middle
-                uint8_t* nxw = ARR(uint8_t, po_next);
-                nxw[pick_prev] = nxw[pick];
-                if (nxw[pick] == kNone) ARR(uint8_t, r_int)[r] = (uint8_t)pick_prev;
+                PORD(uint8_t, next, pick_prev) = PORD(uint8_t, next, pick);
+                if (PORD(uint8_t, next, pick) == kNone) RES(uint8_t, int, r) = (uint8_t)pick_prev;
             } else {
-                list_pop(ARR(uint8_t, r_inh) + r, ARR(uint8_t, r_int) + r, ARR(uint8_t, po_next));
+                list_pop<kPoStride>(&RES(uint8_t, inh, r), &RES(uint8_t, int, r), PO_NEXT);
             }
         } else {
-            list_pop(ARR(uint8_t, r_inh) + r, ARR(uint8_t, r_int) + r, ARR(uint8_t, po_next));
+            list_pop<kPoStride>(&RES(uint8_t, inh, r), &RES(uint8_t, int, r), PO_NEXT);
         }
-        ARR(uint8_t, po_loc)[pick] = LOC_NONE;
+        PORD(uint8_t, loc, pick) = LOC_NONE;
         if (chain) return pick;
         pushN(EV(OP_MACH_GOT, r, pick));
         return kNone;
     }
     // _breakdowns entry: draw the repair time and sleep   factory_sim.py:267-276
     __device__ __forceinline__ void breakdown_start(int r) {
-        ARR(float, r_start)[r] = now;                                      // breakdown_start, :272
+        RES(float, start, r) = now;                                      // breakdown_start, :272
         float ttr = draw_scalar(3, TAB(DDist, t_ttr)[r]);                  // :275
         if (DBR) ARR(uint8_t, r_flags)[r] &= ~F_TIMER_PY;
         timer(r, __fadd_rn(now, ttr), EV(OP_TO_TTR, r, 0), ttr > 0.0f);      // max(0, np.float32(v)) is the int 0 for v <= 0
     }
     // _production_system loop top   factory_sim.py:375-380
     __device__ __forceinline__ void mach_loop_top(int r) {
-        if (ARR(float, r_utf)[r] >= ARR(float, r_tbf)[r]) { breakdown_start(r); return; }
+        if (RES(float, utf, r) >= RES(float, tbf, r)) { breakdown_start(r); return; }
         mach_select(r);
     }
 
@@ -464,6 +522,7 @@ struct Sim {
         int a = (ev >> 8) & 0xFF;
         int b = (ev >> 16) & 0xFF;
         nev++;
+        uint32_t tail_ev;
         switch (op) {
         case OP_TO_WARMUP:                                       // factory_sim.py:97-99
             warm = 1;
@@ -472,103 +531,103 @@ struct Sim {
         case OP_TO_DEMAND: {                                     // :166-175
             uint32_t d = alloc_do();
             if (status) break;
-            ARR(uint8_t, do_prod)[d] = (uint8_t)a;
-            ARR(float, do_qty)[d] = ARR(float, p_dqty)[a];
-            ARR(float, do_due)[d] = __fadd_rn(ARR(float, p_ddue)[a], now);
-            ARR(float, do_arr)[d] = now;
-            list_append(&sc->inb_head, &sc->inb_tail, ARR(uint8_t, do_next), d);
-            if (!alone()) { pushN(EV(OP_PUT_INBOUND, a, 0)); break; }
+            DORD(uint8_t, prod, d) = (uint8_t)a;
+            DORD(float, qty, d) = PRD(float, dqty, a);
+            DORD(float, due, d) = __fadd_rn(PRD(float, ddue, a), now);
+            DORD(float, arr, d) = now;
+            list_append<kDoStride>(&sc->inb_head, &sc->inb_tail, DO_NEXT, d);
+            if (!alone()) PUSH_AND_LEAVE(EV(OP_PUT_INBOUND, a, 0))
             nev++;                                               // StorePut[inbound] popped right away
         }
         // fall through
         case OP_PUT_INBOUND:                                     // StorePut[inbound] processed
             if (sc->sched_wait && sc->inb_head != kNone) {
-                uint32_t d = list_pop(&sc->inb_head, &sc->inb_tail, ARR(uint8_t, do_next));
+                uint32_t d = list_pop<kDoStride>(&sc->inb_head, &sc->inb_tail, DO_NEXT);
                 sc->sched_wait = 0;
                 pushN(EV(OP_SCHED_GOT, 0, d));
             }
             demand_draw(a);
             break;
         case OP_SCHED_GOT: {                                     // scheduler :183-193
-            int prod = ARR(uint8_t, do_prod)[b];
+            int prod = DORD(uint8_t, prod, b);
             if (!DBR) {           // DBR: _process_demandOrders only forwards (toc_dbr/simulation.py:408-412)
                 uint32_t po = alloc_po();
                 if (status) break;
-                ARR(uint8_t, po_prod)[po] = (uint8_t)prod;
-                ARR(float, po_qty)[po] = ARR(float, do_qty)[b];
-                if (POLICY == MSIM_POLICY_MAX_PRIORITY) ARR(float, po_prio)[po] = 0.0f;
-                if (POLICY == MSIM_POLICY_EDD) ARR(float, po_prio)[po] = -ARR(float, do_due)[b];
+                PORD(uint8_t, prod, po) = (uint8_t)prod;
+                PORD(float, qty, po) = DORD(float, qty, b);
+                if (POLICY == MSIM_POLICY_MAX_PRIORITY) PORD(float, prio, po) = 0.0f;
+                if (POLICY == MSIM_POLICY_EDD) PORD(float, prio, po) = -DORD(float, due, b);
                 pushU(EV(OP_INIT_RELEASE, 0, po));
             }
-            list_append(ARR(uint8_t, p_obh) + prod, ARR(uint8_t, p_obt) + prod, ARR(uint8_t, do_next), b);
+            list_append<kDoStride>(&PRD(uint8_t, obh, prod), &PRD(uint8_t, obt, prod), DO_NEXT, b);
             pushN(EV(OP_PUT_OUTBOUND, prod, 0));
             break;
         }
         case OP_PUT_OUTBOUND:                                    // StorePut[outbound[p]] processed
-            if (((sc->deliv_wait >> a) & 1u) && ARR(uint8_t, p_obh)[a] != kNone) {
-                uint32_t d = list_pop(ARR(uint8_t, p_obh) + a, ARR(uint8_t, p_obt) + a, ARR(uint8_t, do_next));
+            if (((sc->deliv_wait >> a) & 1u) && PRD(uint8_t, obh, a) != kNone) {
+                uint32_t d = list_pop<kDoStride>(&PRD(uint8_t, obh, a), &PRD(uint8_t, obt, a), DO_NEXT);
                 sc->deliv_wait &= ~(1u << a);
                 pushN(EV(OP_DELIV_GOT, a, d));
             }
             sched_get();
             break;
         case OP_INIT_RELEASE: {                                  // _release_order :195-211
-            int prod = ARR(uint8_t, po_prod)[b];
+            int prod = PORD(uint8_t, prod, b);
             int first = TAB(uint8_t, t_step_res)[TAB(uint16_t, t_route_start)[prod]];
-            ARR(uint8_t, po_done)[b] = 0;
-            ARR(float, po_rel)[b] = now;
+            PORD(uint8_t, done, b) = 0;
+            PORD(float, rel, b) = now;
             if (DBR) ARR(uint8_t, po_relpy)[b] = (uint8_t)now_py;
-            list_append(ARR(uint8_t, r_inh) + first, ARR(uint8_t, r_int) + first, ARR(uint8_t, po_next), b);
-            ARR(uint8_t, po_loc)[b] = LOC_IN;
-            if (!alone()) { pushN(EV(OP_REL_PUT1, first, b)); break; }
+            list_append<kPoStride>(&RES(uint8_t, inh, first), &RES(uint8_t, int, first), PO_NEXT, b);
+            PORD(uint8_t, loc, b) = LOC_IN;
+            if (!alone()) PUSH_AND_LEAVE(EV(OP_REL_PUT1, first, b))
             a = first;
             nev++;                                               // StorePut[input of the first resource] popped right away
         }
         // fall through
         case OP_REL_PUT1: {                                      // :211-212
             serve_mach(a);
-            float q = ARR(float, po_qty)[b];
+            float q = PORD(float, qty, b);
             if (!(q > 0.0f)) { fail(MSIM_ST_AMOUNT_NONPOSITIVE); break; }
-            int prod = ARR(uint8_t, po_prod)[b];
-            ARR(float, p_wip)[prod] = __fadd_rn(ARR(float, p_wip)[prod], q);
-            if (!alone()) { pushN(EV(OP_REL_PUT2, a, b)); break; }
+            int prod = PORD(uint8_t, prod, b);
+            PRD(float, wip, prod) = __fadd_rn(PRD(float, wip, prod), q);
+            if (!alone()) PUSH_AND_LEAVE(EV(OP_REL_PUT2, a, b))
             nev++;                                               // ContainerPut[wip] popped right away
         }
         // fall through
         case OP_REL_PUT2: {                                      // :214-242
-            float q = ARR(float, po_qty)[b];
-            int prod = ARR(uint8_t, po_prod)[b];
+            float q = PORD(float, qty, b);
+            int prod = PORD(uint8_t, prod, b);
             sc->tot_wip = __fadd_rn(sc->tot_wip, q);
-            if (p.log_queues) ARR(float, r_qq)[a] = __fadd_rn(ARR(float, r_qq)[a], q);
+            if (LOGQ) ARR(float, r_qq)[a] = __fadd_rn(ARR(float, r_qq)[a], q);
             if (warm) {
                 emit(ringP(PM_RELEASED, prod), now, q);
                 inventory(prod, true, false);
-                if (p.log_queues) queue_log_add(a, q);
+                if (LOGQ) queue_log_add(a, q);
             }
             nev++;                                               // process-end event
             break;
         }
         case OP_MACH_GOT:                                        // _production_system :380-395
         L_MACH_GOT: {
-            if (p.log_queues) {
-                float q = ARR(float, po_qty)[b];
+            if (LOGQ) {
+                float q = PORD(float, qty, b);
                 ARR(float, r_qq)[a] = __fsub_rn(ARR(float, r_qq)[a], q);
                 if (warm) {
                     emit(ringR(RM_QUEUE, a), now, ARR(float, r_qq)[a]);
                     ARR(float, r_lastq)[a] = ARR(float, r_qq)[a];
                 }
             }
-            ARR(uint8_t, r_cur)[a] = (uint8_t)b;
-            ARR(uint8_t, po_loc)[b] = LOC_PROC;
-            if (!(force || alone())) { pushN(EV(OP_MACH_PUTPROC, a, 0)); break; }
+            RES(uint8_t, cur, a) = (uint8_t)b;
+            PORD(uint8_t, loc, b) = LOC_PROC;
+            if (!(force || alone())) PUSH_AND_LEAVE(EV(OP_MACH_PUTPROC, a, 0))
             nev++;                                               // StorePut[processing] popped right away
         }
         // fall through
         case OP_MACH_PUTPROC: {                                  // :397-421 (setup drawn on every operation, quirk E1)
             float setup = draw_scalar_hot(1, TAB(DDist, t_setup)[a]);
-            ARR(float, r_setup)[a] = setup;
+            RES(float, setup, a) = setup;
             if (warm) emit(ringR(RM_SETUP, a), now, setup);
-            if (!(force || alone())) { pushN(EV(OP_MACH_REQ, a, 0)); break; }
+            if (!(force || alone())) PUSH_AND_LEAVE(EV(OP_MACH_REQ, a, 0))
             nev++;                                               // Request popped right away
         }
         // fall through
@@ -577,8 +636,8 @@ struct Sim {
             force = 0;
             if (DBR) ARR(uint8_t, r_flags)[a] &= ~F_TIMER_PY;
             {
-                const float t = __fadd_rn(now, ARR(float, r_setup)[a]);
-                const bool f32 = (ARR(float, r_setup)[a] > 0.0f);                  // a positive setup is a numpy float32, a zero one the int 0
+                const float t = __fadd_rn(now, RES(float, setup, a));
+                const bool f32 = (RES(float, setup, a) > 0.0f);                  // a positive setup is a numpy float32, a zero one the int 0
                 if (ahead && t == now) {
                     // The setup Timeout lands on the current timestamp, so the machine goes on within it -- and SimPy
                     // schedules that Timeout only after the first three transport events (TRANS_GOT, TRANS_PUT,
@@ -594,12 +653,13 @@ struct Sim {
             }
         }
             // fall through
-        case OP_TO_SETUP: {                                      // :425-440
-            uint32_t po = ARR(uint8_t, r_cur)[a];
-            int prod = ARR(uint8_t, po_prod)[po];
-            int step = TAB(uint16_t, t_route_start)[prod] + ARR(uint8_t, po_done)[po];
-            ARR(float, r_start)[a] = now;
-            double total = draw_batch(TAB(DDist, t_step_dist)[step], (int)ARR(float, po_qty)[po]);
+        case OP_TO_SETUP:
+        {                                      // :425-440
+            uint32_t po = RES(uint8_t, cur, a);
+            int prod = PORD(uint8_t, prod, po);
+            int step = TAB(uint16_t, t_route_start)[prod] + PORD(uint8_t, done, po);
+            RES(float, start, a) = now;
+            double total = draw_batch(TAB(DDist, t_step_dist)[step], (int)PORD(float, qty, po));
             if (total < 0.0) { fail(MSIM_ST_NEGATIVE_DELAY); break; }
             if (DBR) {
                 uint8_t fl = ARR(uint8_t, r_flags)[a] & ~(F_TIMER_PY | F_START_PY);
@@ -625,8 +685,9 @@ struct Sim {
             timer(a, __fadd_rn(now, __double2float_rn(total)), EV(OP_TO_PROC, a, 0));
             break;
         }
-        case OP_TO_PROC: {                                       // :442-451
-            uint32_t po = ARR(uint8_t, r_cur)[a];
+        case OP_TO_PROC:
+        {                                       // :442-451
+            uint32_t po = RES(uint8_t, cur, a);
             float busy;
             if (DBR && now_py && (ARR(uint8_t, r_flags)[a] & F_START_PY)) {
                 // both ends python-typed: float64 subtraction and python round (factory_sim.py:443)
@@ -635,27 +696,27 @@ struct Sim {
                 if (ARR(uint8_t, r_flags)[a] & F_UTF_PY) {
                     double u = __dadd_rn(ARR(double, r_utf_d)[a], bd);
                     ARR(double, r_utf_d)[a] = u;
-                    ARR(float, r_utf)[a] = __double2float_rn(u);
+                    RES(float, utf, a) = __double2float_rn(u);
                 } else {
-                    ARR(float, r_utf)[a] = __fadd_rn(ARR(float, r_utf)[a], busy);
+                    RES(float, utf, a) = __fadd_rn(RES(float, utf, a), busy);
                 }
             } else {
-                busy = round6(__fsub_rn(now, ARR(float, r_start)[a]));
-                ARR(float, r_utf)[a] = __fadd_rn(ARR(float, r_utf)[a], busy);
+                busy = round6(__fsub_rn(now, RES(float, start, a)));
+                RES(float, utf, a) = __fadd_rn(RES(float, utf, a), busy);
                 if (DBR) ARR(uint8_t, r_flags)[a] &= ~F_UTF_PY;
             }
-            ARR(float, r_busy)[a] = busy;
-            ARR(uint8_t, po_done)[po]++;
-            ARR(uint8_t, po_loc)[po] = LOC_NONE;
-            if (!alone()) { pushN(EV(OP_MACH_GOTPROC, a, 0)); break; }
+            RES(float, busy, a) = busy;
+            PORD(uint8_t, done, po)++;
+            PORD(uint8_t, loc, po) = LOC_NONE;
+            if (!alone()) PUSH_AND_LEAVE(EV(OP_MACH_GOTPROC, a, 0))
             nev++;                                               // StoreGet[processing] popped right away
         }
         // fall through
         case OP_MACH_GOTPROC: {                                  // :452
-            uint32_t po = ARR(uint8_t, r_cur)[a];
-            list_append(ARR(uint8_t, r_outh) + a, ARR(uint8_t, r_outt) + a, ARR(uint8_t, po_next), po);
-            ARR(uint8_t, po_loc)[po] = LOC_OUT;
-            if (!alone()) { pushN(EV(OP_MACH_PUTOUT, a, 0)); break; }
+            uint32_t po = RES(uint8_t, cur, a);
+            list_append<kPoStride>(&RES(uint8_t, outh, a), &RES(uint8_t, outt, a), PO_NEXT, po);
+            PORD(uint8_t, loc, po) = LOC_OUT;
+            if (!alone()) PUSH_AND_LEAVE(EV(OP_MACH_PUTOUT, a, 0))
             nev++;                                               // StorePut[output] popped right away
         }
         // fall through
@@ -665,20 +726,20 @@ struct Sim {
             // / draws / calendar entries in the same relative order whether interleaved event by event (SimPy) or run
             // one after the other, so the machine chain may run right here.  Not for DBR (its dispatch scans observe
             // order locations) nor with queue logging (both chains write `queue` records).
-            const bool solo = !DBR && !p.log_queues && alone();
-            if (((sc->trans_wait >> a) & 1u) && ARR(uint8_t, r_outh)[a] != kNone) {
-                uint32_t po = list_pop(ARR(uint8_t, r_outh) + a, ARR(uint8_t, r_outt) + a, ARR(uint8_t, po_next));
-                ARR(uint8_t, po_loc)[po] = LOC_NONE;
+            const bool solo = !DBR && !LOGQ && alone();
+            if (((sc->trans_wait >> a) & 1u) && RES(uint8_t, outh, a) != kNone) {
+                uint32_t po = list_pop<kPoStride>(&RES(uint8_t, outh, a), &RES(uint8_t, outt, a), PO_NEXT);
+                PORD(uint8_t, loc, po) = LOC_NONE;
                 sc->trans_wait &= ~(1u << a);
                 pushN(EV(OP_TRANS_GOT, a, po));
             }
             if (DBR && p.dbr_repair && a == p.dbr_ccr) {        // patch P3: stores.resource_finished[CCR].put(po)
-                if (sc->fin_n < 5) sc->fin[sc->fin_n++] = ARR(uint8_t, r_cur)[a]; else fail(MSIM_ST_FIFO_OVERFLOW);
+                if (sc->fin_n < 5) sc->fin[sc->fin_n++] = RES(uint8_t, cur, a); else fail(MSIM_ST_FIFO_OVERFLOW);
                 pushN(EV(OP_FIN_PUT, 0, 0));
             }
-            if (warm) emit(ringR(RM_UTIL, a), now, ARR(float, r_busy)[a]);
+            if (warm) emit(ringR(RM_UTIL, a), now, RES(float, busy, a));
             nev++;                                               // Release event of the `with` block
-            if (ARR(float, r_utf)[a] >= ARR(float, r_tbf)[a]) { breakdown_start(a); break; }   // breakdown first (:376-377)
+            if (RES(float, utf, a) >= RES(float, tbf, a)) { breakdown_start(a); break; }   // breakdown first (:376-377)
             {
                 const bool chain = solo && (attn & ~A_FLUSH) == 0u;
                 uint32_t pick = mach_select(a, chain);
@@ -690,43 +751,43 @@ struct Sim {
             }
         }
         case OP_TO_TTR:                                          // _breakdowns :277-289
-            if (warm) emit(ringR(RM_BREAKDOWN, a), ARR(float, r_start)[a], round6(__fsub_rn(now, ARR(float, r_start)[a])));
-            ARR(float, r_tbf)[a] = draw_scalar(3, TAB(DDist, t_tbf)[a]);
-            ARR(float, r_utf)[a] = 0.0f;
+            if (warm) emit(ringR(RM_BREAKDOWN, a), RES(float, start, a), round6(__fsub_rn(now, RES(float, start, a))));
+            RES(float, tbf, a) = draw_scalar(3, TAB(DDist, t_tbf)[a]);
+            RES(float, utf, a) = 0.0f;
             if (DBR) { ARR(double, r_utf_d)[a] = 0.0; ARR(uint8_t, r_flags)[a] |= F_UTF_PY; }   // the int 0
             mach_select(a);
             break;
         case OP_TRANS_GOT:                                       // _transportation :300-304
-            ARR(uint8_t, r_tcur)[a] = (uint8_t)b;
-            ARR(uint8_t, po_loc)[b] = LOC_TRANS;
-            if (!alone()) { pushN(EV(OP_TRANS_PUT, a, 0)); break; }
+            RES(uint8_t, tcur, a) = (uint8_t)b;
+            PORD(uint8_t, loc, b) = LOC_TRANS;
+            if (!alone()) PUSH_AND_LEAVE(EV(OP_TRANS_PUT, a, 0))
             nev++;                                               // StorePut[transport] popped right away
             // fall through
         case OP_TRANS_PUT: {                                     // :306-310 / :329-335
-            uint32_t po = ARR(uint8_t, r_tcur)[a];
-            int prod = ARR(uint8_t, po_prod)[po];
+            uint32_t po = RES(uint8_t, tcur, a);
+            int prod = PORD(uint8_t, prod, po);
             int total = TAB(uint16_t, t_route_start)[prod + 1] - TAB(uint16_t, t_route_start)[prod];
-            ARR(uint8_t, po_loc)[po] = LOC_NONE;
-            const bool last = ARR(uint8_t, po_done)[po] == total;
-            if (last || !alone()) { pushN(EV(last ? OP_TRANS_GOT2_FINAL : OP_TRANS_GOT2_NEXT, a, 0)); break; }
+            PORD(uint8_t, loc, po) = LOC_NONE;
+            const bool last = PORD(uint8_t, done, po) == total;
+            if (last || !alone()) PUSH_AND_LEAVE(EV(last ? OP_TRANS_GOT2_FINAL : OP_TRANS_GOT2_NEXT, a, 0))
             nev++;                                               // StoreGet[transport] popped right away
         }
         // fall through
         case OP_TRANS_GOT2_NEXT: {                               // :330-336
-            uint32_t po = ARR(uint8_t, r_tcur)[a];
-            int prod = ARR(uint8_t, po_prod)[po];
-            int nxt = TAB(uint8_t, t_step_res)[TAB(uint16_t, t_route_start)[prod] + ARR(uint8_t, po_done)[po]];
-            list_append(ARR(uint8_t, r_inh) + nxt, ARR(uint8_t, r_int) + nxt, ARR(uint8_t, po_next), po);
-            ARR(uint8_t, po_loc)[po] = LOC_IN;
-            if (!alone()) { pushN(EV(OP_TRANS_PUTIN, a, nxt)); break; }
+            uint32_t po = RES(uint8_t, tcur, a);
+            int prod = PORD(uint8_t, prod, po);
+            int nxt = TAB(uint8_t, t_step_res)[TAB(uint16_t, t_route_start)[prod] + PORD(uint8_t, done, po)];
+            list_append<kPoStride>(&RES(uint8_t, inh, nxt), &RES(uint8_t, int, nxt), PO_NEXT, po);
+            PORD(uint8_t, loc, po) = LOC_IN;
+            if (!alone()) PUSH_AND_LEAVE(EV(OP_TRANS_PUTIN, a, nxt))
             b = nxt;
             nev++;                                               // StorePut[input of the next resource] popped right away
         }
         // fall through
         case OP_TRANS_PUTIN: {                                   // :336-358
             serve_mach(b);
-            if (p.log_queues) {
-                float q = ARR(float, po_qty)[ARR(uint8_t, r_tcur)[a]];
+            if (LOGQ) {
+                float q = PORD(float, qty, RES(uint8_t, tcur, a));
                 ARR(float, r_qq)[b] = __fadd_rn(ARR(float, r_qq)[b], q);
                 if (warm) queue_log_add(b, q);
             }
@@ -734,37 +795,37 @@ struct Sim {
             break;
         }
         case OP_TRANS_GOT2_FINAL: {                              // :311
-            uint32_t po = ARR(uint8_t, r_tcur)[a];
-            int prod = ARR(uint8_t, po_prod)[po];
-            ARR(float, p_fg)[prod] = __fadd_rn(ARR(float, p_fg)[prod], ARR(float, po_qty)[po]);
-            if (!alone()) { pushN(EV(OP_TRANS_FGPUT, a, 0)); break; }
+            uint32_t po = RES(uint8_t, tcur, a);
+            int prod = PORD(uint8_t, prod, po);
+            PRD(float, fg, prod) = __fadd_rn(PRD(float, fg, prod), PORD(float, qty, po));
+            if (!alone()) PUSH_AND_LEAVE(EV(OP_TRANS_FGPUT, a, 0))
             nev++;                                               // ContainerPut[finished goods] popped right away
         }
         // fall through
         case OP_TRANS_FGPUT: {                                   // ContainerPut[FG] processed, then :312
-            uint32_t po = ARR(uint8_t, r_tcur)[a];
-            int prod = ARR(uint8_t, po_prod)[po];
+            uint32_t po = RES(uint8_t, tcur, a);
+            int prod = PORD(uint8_t, prod, po);
             serve_fg(prod);
-            float q = ARR(float, po_qty)[po];
-            float w = ARR(float, p_wip)[prod];
+            float q = PORD(float, qty, po);
+            float w = PRD(float, wip, prod);
             if (!(w >= q)) { fail(MSIM_ST_WIP_GET_BLOCKED); break; }
-            ARR(float, p_wip)[prod] = __fsub_rn(w, q);
-            if (!alone()) { pushN(EV(OP_TRANS_WIPGET, a, 0)); break; }
+            PRD(float, wip, prod) = __fsub_rn(w, q);
+            if (!alone()) PUSH_AND_LEAVE(EV(OP_TRANS_WIPGET, a, 0))
             nev++;                                               // ContainerGet[wip] popped right away
         }
         // fall through
         case OP_TRANS_WIPGET: {                                  // :314-326
-            uint32_t po = ARR(uint8_t, r_tcur)[a];
-            int prod = ARR(uint8_t, po_prod)[po];
-            sc->tot_wip = __fsub_rn(sc->tot_wip, ARR(float, po_qty)[po]);
-            float f = ARR(float, p_fg)[prod];
-            float old = ARR(float, p_fgc)[prod];
-            ARR(float, p_fgc)[prod] = f;
+            uint32_t po = RES(uint8_t, tcur, a);
+            int prod = PORD(uint8_t, prod, po);
+            sc->tot_wip = __fsub_rn(sc->tot_wip, PORD(float, qty, po));
+            float f = PRD(float, fg, prod);
+            float old = PRD(float, fgc, prod);
+            PRD(float, fgc, prod) = f;
             sc->fgc_sum = __fadd_rn(sc->fgc_sum, __fsub_rn(f, old));
             if (warm) {
-                float flow = __fsub_rn(now, ARR(float, po_rel)[po]);
+                float flow = __fsub_rn(now, PORD(float, rel, po));
                 if (DBR && now_py && ARR(uint8_t, po_relpy)[po])
-                    flow = __double2float_rn(__dsub_rn(now_d, (double)ARR(float, po_rel)[po]));
+                    flow = __double2float_rn(__dsub_rn(now_d, (double)PORD(float, rel, po)));
                 emit(ringP(PM_FLOW, prod), now, flow);
                 inventory(prod, true, true);
             }
@@ -780,7 +841,7 @@ struct Sim {
             // (one finished_goods.get() site for the three delivery modes and the onDue timer: the handler switch is
             //  instruction-cache bound, inlined copies cost more than the branches)
             if (p.delivery_mode == MSIM_DELIVERY_INSTANTLY) {
-                if (!(ARR(float, p_fg)[a] >= ARR(float, do_qty)[b])) {      // lost sale: nothing is taken
+                if (!(PRD(float, fg, a) >= DORD(float, qty, b))) {      // lost sale: nothing is taken
                     if (warm) {
                         inventory(a, false, true);
                         delivery_records(b, a, false);
@@ -790,7 +851,7 @@ struct Sim {
                     break;
                 }
             } else if (p.delivery_mode == MSIM_DELIVERY_ON_DUE) {
-                float wait = __fsub_rn(ARR(float, do_due)[b], now);
+                float wait = __fsub_rn(DORD(float, due, b), now);
                 if (wait > 0.0f) {
                     float t = __fadd_rn(now, wait);
                     if (t == now) {
@@ -852,10 +913,10 @@ struct Sim {
             break;
         case OP_DRAIN_GOT:                                       // _update_constraint_buffer :173-190
             if (DBR) {
-                int prod = ARR(uint8_t, po_prod)[b];
-                int step = TAB(uint16_t, t_route_start)[prod] + ARR(uint8_t, po_done)[b] - 1;
+                int prod = PORD(uint8_t, prod, b);
+                int step = TAB(uint16_t, t_route_start)[prod] + PORD(uint8_t, done, b) - 1;
                 float mean_pt = __double2float_rn(TAB(DDist, t_step_dist)[step].raw0);
-                float ccr_time = __fadd_rn(__fmul_rn(mean_pt, ARR(float, po_qty)[b]), __double2float_rn(p.dbr_ccr_setup));
+                float ccr_time = __fadd_rn(__fmul_rn(mean_pt, PORD(float, qty, b)), __double2float_rn(p.dbr_ccr_setup));
                 sc->cb_level = __fsub_rn(sc->cb_level, ccr_time);
                 if (sc->fin_n) {
                     uint32_t po = sc->fin[0];
@@ -874,11 +935,14 @@ struct Sim {
         default:
             break;
         }
+        return;
+    L_TAIL_PUSH:
+        pushN(tail_ev);
     }
 
     // process_order continuation: constraint_buffer_level += ccr_add; env.process(_release_order(po))
     __device__ __forceinline__ void dorder_go(int po) {
-        sc->cb_level = __fadd_rn(sc->cb_level, ARR(float, po_ccr)[po]);
+        sc->cb_level = __fadd_rn(sc->cb_level, PORD(float, ccr, po));
         pushU(EV(OP_INIT_RELEASE, 0, po));
         nev++;                                                   // process-end event
     }
@@ -890,7 +954,7 @@ struct Sim {
         uint8_t ord[32];
         for (int i = 0; i < P; ++i) {
             float target = __double2float_rn(TAB(double, t_shipbuf)[i]);
-            float have = __fadd_rn(ARR(float, p_wip)[i], ARR(float, p_fg)[i]);
+            float have = __fadd_rn(PRD(float, wip, i), PRD(float, fg, i));
             float repl = __fsub_rn(target, have);
             if (!(repl > 0.0f)) repl = 0.0f;
             float lot = __double2float_rn(p.dbr_min_lot);
@@ -922,10 +986,10 @@ struct Sim {
                 if (qty[i] > 0.0f && go) {
                     uint32_t po = alloc_po();
                     if (status) return;
-                    ARR(uint8_t, po_prod)[po] = (uint8_t)i;
-                    ARR(float, po_qty)[po] = qty[i];
+                    PORD(uint8_t, prod, po) = (uint8_t)i;
+                    PORD(float, qty, po) = qty[i];
                     ARR(float, po_tt)[po] = sched;               // holds `schedule` until Initialize[process_order]
-                    ARR(float, po_ccr)[po] = ccr_t;
+                    PORD(float, ccr, po) = ccr_t;
                     pushU(EV(OP_INIT_DORDER, 0, po));
                     room = __fsub_rn(room, ccr_t);
                 }
@@ -981,7 +1045,7 @@ struct Sim {
         now_d = 0.0; now_py = 1; sel_req = 0;
         for (int r = 0; r < R; ++r) {                            // _start_resources :248-261 (draws at construction)
             const DDist& tb_ = TAB(DDist, t_tbf)[r];
-            ARR(float, r_tbf)[r] = tb_.kind == MSIM_DIST_NONE ? CUDART_INF_F : draw_scalar(3, tb_);
+            RES(float, tbf, r) = tb_.kind == MSIM_DIST_NONE ? CUDART_INF_F : draw_scalar(3, tb_);
         }
         nev++;                                                   // Initialize[warmup]
         timer(R + P, p.warmup, EV(OP_TO_WARMUP, 0, 0), false);
@@ -1004,7 +1068,7 @@ struct Sim {
                 nev++;
                 float sbuf = __double2float_rn(TAB(double, t_shipbuf)[prod]);
                 if (!(sbuf > 0.0f)) { fail(MSIM_ST_AMOUNT_NONPOSITIVE); return; }
-                ARR(float, p_fg)[prod] = sbuf;
+                PRD(float, fg, prod) = sbuf;
                 pushN(EV(OP_SEED_PUT, prod, 0));
             }
             pending = EV(OP_TO_TICK, 0, 0) | EV_PY; attn |= A_PENDING;   // Initialize[scheduler] (the rope): first tick at t = 0,
@@ -1013,9 +1077,46 @@ struct Sim {
         nev++;                                                   // Initialize[scheduler]
         sc->sched_wait = 1;
     }
-#undef ARR
-#undef TAB
 };
+
+// DBR only (python-typed clock): the order of calendar entries that share one float32 timestamp.
+// SimPy's heap compares the time OBJECTS pairwise: two python floats compare exactly (float64); as soon as one side is a
+// numpy float32 the python float is rounded to float32 first (NEP 50), the times tie and (priority, eid) decides
+// (examples/toc_dbr/simulation.py:200-289 on simpy core's heap of (time, priority, eid, event) tuples).  `slot` is the
+// entry with the smallest eid among those tied on the float32 bits `tbits`.  If that entry is python-typed, a python-
+// typed entry of the same float32 cell with a smaller float64 time precedes it; the entry chosen that way still has to
+// wait for the python-typed zero-delay events of an EARLIER float64 instant of the cell (`head_py`: the NORMAL fifo
+// is not empty and its head is python-typed): then -1 is returned and the caller runs that event first.
+// Runs on lane 0 only, a few times per 10^5 events (several calendar entries inside one float32 spacing of the clock).
+__device__ __noinline__ int dbr_cell_order(const KParams& p, const unsigned char* sb, const Scal* sc, uint32_t tbits,
+                                           int slot, double now_d, bool head_py) {
+    const Lay& L = p.lay;
+    const int R = L.R, P = L.P;
+    if (slot >= L.NT) return slot;                               // order timers are float32-typed Timeouts
+    const uint32_t* tt = reinterpret_cast<const uint32_t*>(sb + L.tm_time);
+    const uint32_t* te = reinterpret_cast<const uint32_t*>(sb + L.tm_eid);
+    const uint8_t* fl = sb + L.r_flags;
+    const double* tpy = reinterpret_cast<const double*>(sb + L.r_tpy);
+    int best = -1;
+    double bd = 0.0;
+    uint32_t be = 0u;
+    for (int i = 0; i < R + P + 2; ++i) {
+        if (tt[i] != tbits) continue;
+        double d;
+        if (i < R) { if (!(fl[i] & F_TIMER_PY)) continue; d = tpy[i]; }
+        else if (i == R + P) d = p.warmup_d;
+        else if (i == R + P + 1) d = sc->tick_d;
+        else continue;                                           // demand generators: float32-typed gaps
+        if (best < 0 || d < bd || (d == bd && te[i] < be)) { best = i; bd = d; be = te[i]; }
+    }
+    if (best < 0) return slot;                                   // no python-typed entry in this cell
+    {   // is the smallest-eid entry itself python-typed?  (otherwise float32 ties decide by eid: keep it)
+        bool slot_py = slot < R ? (fl[slot] & F_TIMER_PY) != 0 : (slot == R + P || slot == R + P + 1);
+        if (!slot_py) return slot;
+    }
+    if (head_py && bd > now_d) return -1;                        // a later float64 instant: the pending events come first
+    return best;
+}
 
 // cooperative log flush: one 128-bit record per lane (st.global.v4, 512 contiguous bytes per warp) into the
 // replication's HBM ring + fused per-ring reductions.  Lanes holding records of the same ring are grouped with
@@ -1045,17 +1146,18 @@ __device__ __forceinline__ void warp_flush(const KParams& p, const unsigned char
 }
 
 // ---------------------------------------------------------------------------------------------------------
-template <int POLICY, int RNG>
-__global__ void __launch_bounds__(256, 5) sim_kernel(const __grid_constant__ KParams p) {
+template <int POLICY, int RNG, int OPTS, int MINB>
+__global__ void __launch_bounds__(256, MINB) sim_kernel(const __grid_constant__ KParams p) {
     MSIM_DYN_SMEM(smem);
     const Lay& L = p.lay;
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
     unsigned char* sb = smem + (size_t)warp * L.slab_bytes;
     Scal* sc = reinterpret_cast<Scal*>(sb + L.scal);
-    Sim<POLICY, RNG> s(p, sb, sc);
+    Sim<POLICY, RNG, OPTS> s(p, sb, sc);
     const bool on_due = p.delivery_mode == MSIM_DELIVERY_ON_DUE;
     constexpr bool DBR = POLICY == MSIM_POLICY_DBR;
+    constexpr int kPoStride = aos_po_stride(POLICY), kDoStride = kAosDoLinkStride;
     const uint32_t until_bits = __float_as_uint(p.run_until);
 
     for (;;) {
@@ -1074,21 +1176,21 @@ __global__ void __launch_bounds__(256, 5) sim_kernel(const __grid_constant__ KPa
         #pragma unroll 1
         for (int i = lane; i < L.MD; i += 32) {
             if (on_due) reinterpret_cast<float*>(sb + L.do_tt)[i] = CUDART_INF_F;
-            (sb + L.do_next)[i] = (uint8_t)(i + 1 < L.MD ? i + 1 : kNone);
+            DORD(uint8_t, next, i) = (uint8_t)(i + 1 < L.MD ? i + 1 : kNone);
         }
         #pragma unroll 1
         for (int i = lane; i < L.MP; i += 32) {
-            (sb + L.po_next)[i] = (uint8_t)(i + 1 < L.MP ? i + 1 : kNone);
+            PORD(uint8_t, next, i) = (uint8_t)(i + 1 < L.MP ? i + 1 : kNone);
             if (DBR) reinterpret_cast<float*>(sb + L.po_tt)[i] = CUDART_INF_F;
         }
         #pragma unroll 1
         for (int i = lane; i < L.R; i += 32) {
-            (sb + L.r_inh)[i] = kNone; (sb + L.r_int)[i] = kNone; (sb + L.r_outh)[i] = kNone; (sb + L.r_outt)[i] = kNone;
-            if (p.log_queues) reinterpret_cast<float*>(sb + L.r_lastq)[i] = CUDART_NAN_F;
+            RES(uint8_t, inh, i) = kNone; RES(uint8_t, int, i) = kNone; RES(uint8_t, outh, i) = kNone; RES(uint8_t, outt, i) = kNone;
+            if (LOGQ) reinterpret_cast<float*>(sb + L.r_lastq)[i] = CUDART_NAN_F;
         }
         #pragma unroll 1
         for (int i = lane; i < L.P; i += 32) {
-            (sb + L.p_obh)[i] = kNone; (sb + L.p_obt)[i] = kNone; (sb + L.p_fgqh)[i] = kNone; (sb + L.p_fgqt)[i] = kNone;
+            PRD(uint8_t, obh, i) = kNone; PRD(uint8_t, obt, i) = kNone; PRD(uint8_t, fgqh, i) = kNone; PRD(uint8_t, fgqt, i) = kNone;
         }
         #pragma unroll 1
         for (int i = lane; i < L.K; i += 32) {
@@ -1132,33 +1234,28 @@ __global__ void __launch_bounds__(256, 5) sim_kernel(const __grid_constant__ KPa
                 // quantity of same-product orders released strictly earlier that sit in ANY input/output/transport/
                 // processing store, plus the FG level, over the shipping buffer; first minimum wins.
                 const int r = __shfl_sync(FULLMASK, (int)s.sel_req, 0) - 1;
-                const uint8_t* nx = sb + L.po_next;
-                const uint8_t* prd = sb + L.po_prod;
-                const uint8_t* loc = sb + L.po_loc;
-                const float* rel = reinterpret_cast<const float*>(sb + L.po_rel);
-                const float* qty = reinterpret_cast<const float*>(sb + L.po_qty);
-                const float* fg = reinterpret_cast<const float*>(sb + L.p_fg);
                 const double* sbuf = reinterpret_cast<const double*>(p.tblob + L.t_shipbuf);
                 uint32_t best = kNone, best_prev = kNone, prev = kNone;
                 float best_pr = 0.0f;
 #pragma unroll 1
-                for (uint32_t o = (sb + L.r_inh)[r]; o != kNone; prev = o, o = nx[o]) {
-                    const int op = prd[o];
-                    const float ro = rel[o];
+                for (uint32_t o = RES(uint8_t, inh, r); o != kNone; prev = o, o = PORD(uint8_t, next, o)) {
+                    const int op = PORD(uint8_t, prod, o);
+                    const float ro = PORD(float, rel, o);
                     float part = 0.0f;
 #pragma unroll 1
                     for (int i = lane; i < L.MP; i += 32)
-                        if (loc[i] != LOC_NONE && prd[i] == op && rel[i] < ro) part += qty[i];
+                        if (PORD(uint8_t, loc, i) != LOC_NONE && PORD(uint8_t, prod, i) == op && PORD(float, rel, i) < ro)
+                            part += PORD(float, qty, i);
 #pragma unroll
                     for (int off = 16; off > 0; off >>= 1) part += __shfl_xor_sync(FULLMASK, part, off);
-                    const float pr = __fdiv_rn(__fadd_rn(part, fg[op]), __double2float_rn(sbuf[op]));
+                    const float pr = __fdiv_rn(__fadd_rn(part, PRD(float, fg, op)), __double2float_rn(sbuf[op]));
                     if (best == kNone || pr < best_pr) { best = o; best_pr = pr; best_prev = prev; }
                 }
                 if (lane == 0) {
-                    uint8_t* nxw = sb + L.po_next;
-                    if (best_prev == kNone) (sb + L.r_inh)[r] = nxw[best]; else nxw[best_prev] = nxw[best];
-                    if (nxw[best] == kNone) (sb + L.r_int)[r] = (uint8_t)best_prev;
-                    (sb + L.po_loc)[best] = LOC_NONE;
+                    const uint8_t after = PORD(uint8_t, next, best);
+                    if (best_prev == kNone) RES(uint8_t, inh, r) = after; else PORD(uint8_t, next, best_prev) = after;
+                    if (after == kNone) RES(uint8_t, int, r) = (uint8_t)best_prev;
+                    PORD(uint8_t, loc, best) = LOC_NONE;
                     s.pushN(EV(OP_MACH_GOT, (uint32_t)r, best));
                     s.sel_req = 0;
                 }
@@ -1231,8 +1328,21 @@ __global__ void __launch_bounds__(256, 5) sim_kernel(const __grid_constant__ KPa
             const uint32_t emin = __reduce_min_sync(FULLMASK, mine ? be : 0xFFFFFFFFu);
             const uint32_t cnt = __reduce_add_sync(FULLMASK, mine ? (uint32_t)leq : 0u);
             const unsigned who = __ballot_sync(FULLMASK, mine && be == emin);
-            const int slot = __shfl_sync(FULLMASK, bslot, __ffs(who) - 1);
-            if (lane == 0) {
+            const int slot0 = __shfl_sync(FULLMASK, bslot, __ffs(who) - 1);
+            int slot = slot0;
+#if !MSIM_X_F32CELL
+            if (DBR && lane == 0 && (cnt > 1u || (s.attn & A_SAME))) {
+                // several calendar entries inside one float32 cell of the clock: python-typed instants order exactly
+                const bool head_py = s.nqh != s.nqt &&
+                    (reinterpret_cast<const uint32_t*>(sb + L.nq)[s.nqh & (uint32_t)(L.NQ - 1)] & EV_PY) != 0u;
+                slot = dbr_cell_order(p, sb, sc, tbits, slot0, s.now_d, head_py);
+                if (slot < 0) {                              // the fifo head belongs to an earlier float64 instant
+                    first_ev = reinterpret_cast<const uint32_t*>(sb + L.nq)[s.nqh & (uint32_t)(L.NQ - 1)];
+                    s.nqh++;
+                }
+            }
+#endif
+            if (lane == 0 && slot >= 0) {
                 if (s.attn & A_SAME) {
                     if (--s.same_left == 0) s.attn &= ~A_SAME;
                 } else {
@@ -1260,7 +1370,7 @@ __global__ void __launch_bounds__(256, 5) sim_kernel(const __grid_constant__ KPa
                     }
                 } else if (slot < L.NT + L.MD) {
                     int d = slot - L.NT;
-                    ev = EV(OP_TO_SHIP, (sb + L.do_prod)[d], d);
+                    ev = EV(OP_TO_SHIP, DORD(uint8_t, prod, d), d);
                     reinterpret_cast<float*>(sb + L.do_tt)[d] = CUDART_INF_F;
                 } else {
                     int po = slot - L.NT - L.MD;
@@ -1295,153 +1405,37 @@ __global__ void __launch_bounds__(256, 5) sim_kernel(const __grid_constant__ KPa
 }
 
 // ---------------------------------------------------------------------------------------------------------
-// per-ring experiment statistics: x = per-replication metric value; out[ring] += {sum x, sum x^2, n}
-__global__ void reduce_kernel(const double* __restrict__ acc_sum, const uint32_t* __restrict__ acc_cnt,
-                              const int32_t* __restrict__ status, long long n_reps, int K, int P, int R, double span,
-                              double* __restrict__ out) {
-    const int ring = blockIdx.x;
-    // metric class: 0 = sum, 1 = sum / span, 2 = mean  (metrics.py:43-67, factory_sim.py:758-763)
-    int cls;
-    if (ring < 3 * P) cls = 0;
-    else if (ring < 11 * P) cls = 2;
-    else if (ring < 11 * P + 3 * R) cls = 1;
-    else cls = 2;
-    double s1 = 0.0, s2 = 0.0, nn = 0.0;
-    for (long long i = threadIdx.x; i < n_reps; i += blockDim.x) {
-        if (status[i] != 0) continue;
-        double s = acc_sum[i * K + ring];
-        uint32_t c = acc_cnt[i * K + ring];
-        double x;
-        if (cls == 0) x = s;
-        else if (cls == 1) x = s / span;
-        else { if (c == 0) continue; x = s / (double)c; }
-        s1 += x; s2 += x * x; nn += 1.0;
-    }
-    __shared__ double sh[3][32];
-    for (int off = 16; off > 0; off >>= 1) {
-        s1 += __shfl_xor_sync(FULLMASK, s1, off);
-        s2 += __shfl_xor_sync(FULLMASK, s2, off);
-        nn += __shfl_xor_sync(FULLMASK, nn, off);
-    }
-    int w = threadIdx.x >> 5, l = threadIdx.x & 31;
-    if (l == 0) { sh[0][w] = s1; sh[1][w] = s2; sh[2][w] = nn; }
-    __syncthreads();
-    if (w == 0) {
-        int nw = blockDim.x >> 5;
-        s1 = l < nw ? sh[0][l] : 0.0; s2 = l < nw ? sh[1][l] : 0.0; nn = l < nw ? sh[2][l] : 0.0;
-        for (int off = 16; off > 0; off >>= 1) {
-            s1 += __shfl_xor_sync(FULLMASK, s1, off);
-            s2 += __shfl_xor_sync(FULLMASK, s2, off);
-            nn += __shfl_xor_sync(FULLMASK, nn, off);
-        }
-        if (l == 0) { out[ring * 3 + 0] += s1; out[ring * 3 + 1] += s2; out[ring * 3 + 2] += nn; }
-    }
-}
-
-// per-VARIABLE experiment statistics (ExperimentMetrics' default, metrics.py:809-816): per replication the per-key
-// metric values are first averaged over the keys (NaN-skipping), then reduced to {sum, sum^2, n} over replications
-__global__ void reduce_variables_kernel(const double* __restrict__ acc_sum, const uint32_t* __restrict__ acc_cnt,
-                                        const int32_t* __restrict__ status, long long n_reps, int K, int P, int R,
-                                        double span, double* __restrict__ out) {
-    const int var = blockIdx.x;                      // 0..10 product metrics, 11..14 resource metrics, 15..17 general
-    int start, count, cls;
-    if (var < 11) { start = var * P; count = P; cls = var < 3 ? 0 : 2; }
-    else if (var < 15) { start = 11 * P + (var - 11) * R; count = R; cls = var < 14 ? 1 : 2; }
-    else { start = 11 * P + 4 * R + (var - 15); count = 1; cls = 2; }
-    double s1 = 0.0, s2 = 0.0, nn = 0.0;
-    for (long long i = threadIdx.x; i < n_reps; i += blockDim.x) {
-        if (status[i] != 0) continue;
-        double tot = 0.0;
-        int valid = 0;
-        for (int k = 0; k < count; ++k) {
-            double s = acc_sum[i * K + start + k];
-            uint32_t c = acc_cnt[i * K + start + k];
-            if (cls == 0) { tot += s; valid++; }
-            else if (cls == 1) { tot += s / span; valid++; }
-            else if (c) { tot += s / (double)c; valid++; }
-        }
-        if (!valid) continue;
-        double x = tot / (double)valid;
-        s1 += x; s2 += x * x; nn += 1.0;
-    }
-    __shared__ double sh[3][32];
-    for (int off = 16; off > 0; off >>= 1) {
-        s1 += __shfl_xor_sync(FULLMASK, s1, off);
-        s2 += __shfl_xor_sync(FULLMASK, s2, off);
-        nn += __shfl_xor_sync(FULLMASK, nn, off);
-    }
-    int w = threadIdx.x >> 5, l = threadIdx.x & 31;
-    if (l == 0) { sh[0][w] = s1; sh[1][w] = s2; sh[2][w] = nn; }
-    __syncthreads();
-    if (w == 0) {
-        int nw = blockDim.x >> 5;
-        s1 = l < nw ? sh[0][l] : 0.0; s2 = l < nw ? sh[1][l] : 0.0; nn = l < nw ? sh[2][l] : 0.0;
-        for (int off = 16; off > 0; off >>= 1) {
-            s1 += __shfl_xor_sync(FULLMASK, s1, off);
-            s2 += __shfl_xor_sync(FULLMASK, s2, off);
-            nn += __shfl_xor_sync(FULLMASK, nn, off);
-        }
-        if (l == 0) { out[var * 3 + 0] += s1; out[var * 3 + 1] += s2; out[var * 3 + 2] += nn; }
-    }
-}
-
-__global__ void test_philox_kernel(const uint32_t* ctr, const uint32_t* key, uint32_t* out, long long n) {
-    long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    uint32_t o[4];
-    philox4x32_10(ctr[4 * i], ctr[4 * i + 1], ctr[4 * i + 2], ctr[4 * i + 3], key[2 * i], key[2 * i + 1], o);
-    for (int k = 0; k < 4; ++k) out[4 * i + k] = o[k];
-}
-
-__global__ void test_variates_kernel(DDist d, uint64_t seed, int stream_id, int batch_count, double* out, long long n) {
-    long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    PhiloxStream s{(uint32_t)seed, (uint32_t)(seed >> 32), (uint32_t)stream_id, (uint32_t)i};
-    XU r = raw_xu(s.k0, s.k1, s.stream, s.draw, 0u);
-    float v;
-    if (d.kind == MSIM_DIST_CONSTANT) {
-        out[i] = batch_count < 0 ? (double)(d.d0 > 0.f ? d.d0 : 0.f) : (double)(batch_count > 0 ? batch_count : 0) * d.raw0;
-        return;
-    }
-    if (batch_count < 0) {
-        v = sample_from_xu(s, d.kind, d.d0, d.d1, d.mt_d, d.mt_c, r);
-        v = v > 0.0f ? v : 0.0f;
-    } else if (batch_count == 0) {
-        v = 0.0f;
-    } else if (batch_count == 1) {
-        v = sample_from_xu(s, d.kind, d.d0, d.d1, d.mt_d, d.mt_c, r);
-        if (d.kind == MSIM_DIST_NORMAL && !(v > 0.0f)) v = 0.0f;
-    } else {
-        v = batch_many(s, d.kind, d.d0, d.d1, batch_count, r);
-    }
-    out[i] = (double)v;
-}
-
-// ---------------------------------------------------------------------------------------------------------
 typedef void (*sim_fn)(const KParams);
-static sim_fn pick(int policy, int rng) {
-    if (policy == MSIM_POLICY_FIFO) return rng == MSIM_RNG_REPLAY ? sim_kernel<MSIM_POLICY_FIFO, MSIM_RNG_REPLAY>
-                                                                  : sim_kernel<MSIM_POLICY_FIFO, MSIM_RNG_PHILOX>;
+template <int OPTS, int MINB>
+static sim_fn pick_rng(int policy, int rng) {
+    if (policy == MSIM_POLICY_FIFO) return rng == MSIM_RNG_REPLAY ? sim_kernel<MSIM_POLICY_FIFO, MSIM_RNG_REPLAY, OPTS, MINB>
+                                                                  : sim_kernel<MSIM_POLICY_FIFO, MSIM_RNG_PHILOX, OPTS, MINB>;
     if (policy == MSIM_POLICY_MAX_PRIORITY)
-        return rng == MSIM_RNG_REPLAY ? sim_kernel<MSIM_POLICY_MAX_PRIORITY, MSIM_RNG_REPLAY>
-                                      : sim_kernel<MSIM_POLICY_MAX_PRIORITY, MSIM_RNG_PHILOX>;
+        return rng == MSIM_RNG_REPLAY ? sim_kernel<MSIM_POLICY_MAX_PRIORITY, MSIM_RNG_REPLAY, OPTS, MINB>
+                                      : sim_kernel<MSIM_POLICY_MAX_PRIORITY, MSIM_RNG_PHILOX, OPTS, MINB>;
     if (policy == MSIM_POLICY_DBR)
-        return rng == MSIM_RNG_REPLAY ? sim_kernel<MSIM_POLICY_DBR, MSIM_RNG_REPLAY>
-                                      : sim_kernel<MSIM_POLICY_DBR, MSIM_RNG_PHILOX>;
+        return rng == MSIM_RNG_REPLAY ? sim_kernel<MSIM_POLICY_DBR, MSIM_RNG_REPLAY, OPTS, MINB>
+                                      : sim_kernel<MSIM_POLICY_DBR, MSIM_RNG_PHILOX, OPTS, MINB>;
     if (policy == MSIM_POLICY_EDD)
-        return rng == MSIM_RNG_REPLAY ? sim_kernel<MSIM_POLICY_EDD, MSIM_RNG_REPLAY>
-                                      : sim_kernel<MSIM_POLICY_EDD, MSIM_RNG_PHILOX>;
+        return rng == MSIM_RNG_REPLAY ? sim_kernel<MSIM_POLICY_EDD, MSIM_RNG_REPLAY, OPTS, MINB>
+                                      : sim_kernel<MSIM_POLICY_EDD, MSIM_RNG_PHILOX, OPTS, MINB>;
     return nullptr;
 }
+// lean: the run uses neither queue records nor tape recording; wide: 64-register build (only compiled lean)
+static sim_fn pick(int policy, int rng, bool lean, bool wide) {
+    if (!lean) return pick_rng<3, 5>(policy, rng);
+    return wide ? pick_rng<0, 4>(policy, rng) : pick_rng<0, 5>(policy, rng);
+}
 
-int sim_kernel_attrs(int policy, int rng_mode, size_t smem, int* regs, int block, int* blocks_per_sm) {
-    sim_fn f = pick(policy, rng_mode);
+int sim_kernel_attrs(int policy, int rng_mode, bool wide, size_t smem, int* regs, int block, int* blocks_per_sm) {
+    // wide = false: the general kernel (its occupancy also holds for the lean one: same launch bounds, less code)
+    sim_fn f = pick(policy, rng_mode, wide, wide);
     if (!f) return MSIM_E_UNSUPPORTED;
     cudaFuncAttributes at;
     if (cudaFuncGetAttributes(&at, f) != cudaSuccess) return MSIM_E_CUDA;
     if (regs) *regs = at.numRegs;
     if (cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return MSIM_E_CUDA;
-    if (blocks_per_sm) {  // NB: launch_sim re-raises the attribute if another handle lowered it
+    if (blocks_per_sm) {
         int nb = 0;
         if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, f, block, smem) != cudaSuccess) return MSIM_E_CUDA;
         *blocks_per_sm = nb;
@@ -1449,39 +1443,31 @@ int sim_kernel_attrs(int policy, int rng_mode, size_t smem, int* regs, int block
     return 0;
 }
 
-int launch_sim(const KParams& p, int policy, int rng_mode, int grid, int block, size_t smem, void* stream) {
-    sim_fn f = pick(policy, rng_mode);
+int launch_sim(const KParams& p, int policy, int rng_mode, bool wide, int grid, int block, size_t smem, void* stream) {
+    // MSIM_NO_LEAN=1 (diagnostic, tests): always launch the general kernel
+    const char* no_lean = getenv("MSIM_NO_LEAN");
+    const bool lean = !p.log_queues && p.a.rec_cap == 0 && !(no_lean && no_lean[0] == '1');
+    sim_fn f = pick(policy, rng_mode, lean, lean && wide);
     if (!f) return MSIM_E_UNSUPPORTED;
-    // the opt-in limit is per function, not per handle: several handles with different slab sizes share a kernel
-    static size_t smem_set[4][2] = {{0, 0}, {0, 0}, {0, 0}, {0, 0}};
-    if (smem > smem_set[policy][rng_mode]) {
-        if (cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return MSIM_E_CUDA;
-        smem_set[policy][rng_mode] = smem;
-    }
+    // The opt-in shared-memory limit is per FUNCTION, not per handle: handles with different slab sizes share a kernel
+    // and msim_create lowers the attribute again while it probes CTA widths, so it is set before every launch (a host-
+    // side attribute write, negligible next to the launch).
+    if (cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return MSIM_E_CUDA;
     MSIM_LAUNCH(f, grid, block, smem, (cudaStream_t)stream, p);
     return cudaGetLastError() == cudaSuccess ? 0 : MSIM_E_CUDA;
 }
 
-int launch_reduce(const double* acc_sum, const uint32_t* acc_cnt, const int32_t* status, int64_t n_reps, int K, int P,
-                  int R, double span, double* out, void* stream) {
-    MSIM_LAUNCH(reduce_kernel, K, 256, 0, (cudaStream_t)stream, acc_sum, acc_cnt, status, n_reps, K, P, R, span, out);
-    return cudaGetLastError() == cudaSuccess ? 0 : MSIM_E_CUDA;
-}
-
-int launch_reduce_variables(const double* acc_sum, const uint32_t* acc_cnt, const int32_t* status, int64_t n_reps, int K,
-                            int P, int R, double span, double* out, void* stream) {
-    MSIM_LAUNCH(reduce_variables_kernel, 18, 256, 0, (cudaStream_t)stream, acc_sum, acc_cnt, status, n_reps, K, P, R, span, out);
-    return cudaGetLastError() == cudaSuccess ? 0 : MSIM_E_CUDA;
-}
-
-int launch_test_philox(const uint32_t* ctr, const uint32_t* key, uint32_t* out, int64_t n) {
-    MSIM_LAUNCH(test_philox_kernel, (unsigned)((n + 127) / 128), 128, 0, (cudaStream_t)0, ctr, key, out, n);
-    return cudaGetLastError() == cudaSuccess ? 0 : MSIM_E_CUDA;
-}
-
-int launch_test_variates(DDist d, uint64_t seed, int stream_id, int batch_count, double* out, int64_t n) {
-    MSIM_LAUNCH(test_variates_kernel, (unsigned)((n + 127) / 128), 128, 0, (cudaStream_t)0, d, seed, stream_id, batch_count, out, n);
-    return cudaGetLastError() == cudaSuccess ? 0 : MSIM_E_CUDA;
-}
+#undef ARR
+#undef TAB
+#undef RES
+#undef PRD
+#undef PORD
+#undef DORD
+#undef PO_NEXT
+#undef DO_NEXT
+#undef LOGQ
+#undef RECORDING
+#undef NOT_RECORDING
+#undef PUSH_AND_LEAVE
 
 } // namespace msim

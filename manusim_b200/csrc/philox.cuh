@@ -56,21 +56,22 @@ __device__ __forceinline__ XU xu_from_words(const uint32_t w[4]) {
 }
 
 // one out-of-line copy per kernel: the simulation kernel is instruction-cache bound, not ALU bound
-__device__ __noinline__ XU raw_xu(uint32_t k0, uint32_t k1, uint32_t stream, uint32_t draw, uint32_t it) {
+// (static: this header is included by two translation units of libmsim.so)
+static __device__ __noinline__ XU raw_xu(uint32_t k0, uint32_t k1, uint32_t stream, uint32_t draw, uint32_t it) {
     uint32_t w[4];
     philox4x32_10(draw, stream, it, 0u, k0, k1, w);
     return xu_from_words(w);
 }
 
 // gamma shape < 1: Gamma(k) = Gamma(k+1) * U^(1/k)
-__device__ __noinline__ float gamma_boost(const PhiloxStream s, float k) {
+static __device__ __noinline__ float gamma_boost(const PhiloxStream s, float k) {
     uint32_t w[4];
     philox4x32_10(s.draw, s.stream, 0xFFFFu, 1u, s.k0, s.k1, w);
     return __powf(u01(w[0]), 1.0f / k);
 }
 
 // Marsaglia-Tsang rejection iterations 1.. (iteration 0 is the precomputed pair); d = kk-1/3, c = 1/sqrt(9d)
-__device__ __noinline__ float gamma_retry(const PhiloxStream s, float d, float c) {
+static __device__ __noinline__ float gamma_retry(const PhiloxStream s, float d, float c) {
     float out = d;
     for (uint32_t it = 1; it < 64u; ++it) {
         XU r = raw_xu(s.k0, s.k1, s.stream, s.draw, it);
@@ -110,7 +111,7 @@ __device__ __forceinline__ float sample_from_xu(const PhiloxStream& s, int kind,
 }
 
 // sums of count > 1 samples (utils.py:83-98): closed forms for gamma/erlang/expo, loops otherwise
-__device__ __noinline__ float batch_many(const PhiloxStream s, int kind, float d0, float d1, int count, XU r) {
+static __device__ __noinline__ float batch_many(const PhiloxStream s, int kind, float d0, float d1, int count, XU r) {
     if (kind == 2 || kind == 3 || kind == 4) {
         float k = kind == 4 ? (float)count : d0 * (float)count;
         float th = kind == 4 ? d0 : d1;

@@ -73,14 +73,12 @@ def make_ctables(t: ScenarioTables):
         keep.append(arr)
         setattr(ct, name, arr)
     ct.run_until, ct.warmup = float(t.run_until), float(t.warmup)
-    ct.run_until_is_int, ct.warmup_is_int = int(isinstance(t.run_until, int)), int(isinstance(t.warmup, int))
     ct.delivery_mode, ct.policy, ct.log_queues = t.delivery_mode, t.policy, int(t.log_queues)
     if t.dbr:
         d = t.dbr
         cpt = np.ascontiguousarray(d["ccr_pt"], dtype=np.float64)
         keep.append(cpt)
         ct.dbr_ccr, ct.dbr_repair = d["ccr"], int(d["repair"])
-        ct.dbr_interval_is_int = int(isinstance(d["interval"], int))
         ct.dbr_interval, ct.dbr_cb_target = float(d["interval"]), d["cb_target"]
         ct.dbr_release_limit, ct.dbr_ccr_limit = d["release_limit"], d["ccr_limit"]
         ct.dbr_min_lot, ct.dbr_ccr_setup = d["min_lot"], d["ccr_setup"]
@@ -293,9 +291,13 @@ class BatchEngine:
 
     def run_host(self, n_reps: int, seed: int = 0, rep_offset: int = 0, tapes=None, rep_seeds=None,
                  out: Optional[BatchResult] = None, n_log_reps: int = 0, log_cap: int = 0,
-                 retry_overflow: bool = True) -> BatchResult:
+                 retry_overflow: bool = True, device_log: Optional[BatchResult] = None, stats=None) -> BatchResult:
         """Host buffers in, host buffers out (H2D + kernel + D2H inside the call, synchronous).  Replications that
-        overflowed the shared-memory pools are re-run on the big-pool twin engine (Philox mode) unless disabled."""
+        overflowed the shared-memory pools are re-run on the big-pool twin engine (Philox mode) unless disabled.
+        `device_log`: a device BatchResult (from alloc) whose record rings the replications stream into -- they stay
+        in HBM; `stats`: device [K,3] float64 tensor the call accumulates the per-ring {sum x, sum x^2, n} into (the
+        vector the ranks allreduce; the reduction skips failed replications, so the re-run of overflowed ones simply
+        adds its own contribution)."""
         torch = self.torch
         if out is None:
             out = self.alloc_host(n_reps, n_log_reps, log_cap)
@@ -323,6 +325,13 @@ class BatchEngine:
             a.log_cap, a.n_log_reps = out.log.shape[1], out.log.shape[0]
         ms = C.c_double(0.0)
         a.kernel_ms = C.pointer(ms)
+        if device_log is not None and device_log.log is not None:
+            if out.log is not None:
+                raise ValueError("host log rings and device_log are mutually exclusive")
+            a.log_dev, a.log_count_dev = device_log.log.data_ptr(), device_log.log_count.data_ptr()
+            a.log_cap_dev, a.n_log_reps_dev = device_log.log.shape[1], device_log.log.shape[0]
+        if stats is not None:
+            a.stats_dev = stats.data_ptr()
         with torch.cuda.device(self.device):
             _lib.check(self.lib.msim_run_host(self.handle, C.byref(a)))
         out.kernel_ms = ms.value
@@ -341,7 +350,7 @@ class BatchEngine:
                     keys = rs.view(np.uint64)[bad]
                 else:
                     keys = rep_keys(seed, bad.astype(np.int64) + rep_offset)
-                sub = self._big.run_host(len(bad), rep_seeds=np.ascontiguousarray(keys), retry_overflow=False)
+                sub = self._big.run_host(len(bad), rep_seeds=np.ascontiguousarray(keys), retry_overflow=False, stats=stats)
                 idx = torch.from_numpy(bad)
                 for f in ("acc_sum", "acc_cnt", "n_events", "n_timeouts", "status"):
                     getattr(out, f)[idx] = getattr(sub, f)

@@ -34,7 +34,9 @@ from __future__ import annotations
 
 import numpy as np
 
-from oracle import minisimpy as simpy
+from oracle.simpy_select import pick as _pick_simpy
+
+simpy, SIMPY_ENGINE = _pick_simpy()      # minisimpy unless ORACLE_SIMPY=real|auto finds the real package
 from oracle.variates import ReferenceVariates, TapeSource
 
 PM = ["deliveredOntime", "deliveredLate", "lostSales", "flowTime", "leadTime", "tardiness",

@@ -134,6 +134,12 @@ def scenario_table():
     # t = 2184.97 (42 differing records up to t = 2301)
     out["dbr_mixed_types"] = dict(cfg=dict(sim_t, run_until=2401, warmup=100), resources=res_t, products=prod,
                                   policy="dbr", seed=4242, patches=["P2", "P3"])
+    # several python-typed (float64) instants inside ONE float32 spacing of the clock: the reference's heap compares two
+    # python floats exactly, so the earlier float64 instant finishes its whole zero-delay cascade before the later one
+    # starts, whatever their eids (a kernel that orders the calendar by float32 time alone interleaves them by eid:
+    # with this seed it diverges at t = 4322.37 -- 39 844 differing records and another step count up to t = 8001)
+    out["dbr_f64_order"] = dict(cfg=dict(sim_t, run_until=5001, warmup=4000), resources=res_t, products=prod,
+                                policy="dbr", seed=8, patches=["P2", "P3"])
     # zero setups and zero-time operations under max-priority dispatch: the machine finishes whole operations inside one
     # timestamp while the transport chain of the previous order is still being processed (event order within a
     # timestamp; the kernel's "machine chain ahead of the transport chain" shortcut needed OP_HOP for this)

@@ -54,9 +54,10 @@ def load_reference():
         return _loaded
     if not reference_available():
         raise RuntimeError("/root/reference is not mounted; golden vectors can only be generated in the build container")
-    from oracle import minisimpy
+    from oracle.simpy_select import pick
 
-    sys.modules.setdefault("simpy", minisimpy)
+    engine, _loaded["simpy_engine"] = pick()      # minisimpy unless ORACLE_SIMPY=real|auto finds the real package
+    sys.modules["simpy"] = engine
     for p in (str(_HERE / "_stubs"), str(REF_ROOT / "src")):
         if p not in sys.path:
             sys.path.insert(0, p)
@@ -181,7 +182,7 @@ def run_reference(sim_cfg: dict, resources: dict, products: dict, seed: int, pol
         "tape_C": np.array(sim.tapes["C"], dtype=np.float64),
         "tape_D": np.array(sim.tapes["D"], dtype=np.float32),
         "steps": int(steps),
-        "steps_counted": int(env.steps),
+        "steps_counted": int(getattr(env, "steps", steps)),
         "now": env.now,
         "error": error,
         "sim": sim,

@@ -32,5 +32,5 @@ ORACLE_POLICY = {"base": "fifo", "simple_scheduler": "max_priority", "dbr": "dbr
 
 GOLDEN_NAMES = ["toy2", "toy2_instantly", "ss_cfg1", "ss_det", "ss_instantly", "ss_lots", "js20_asready",
                 "js20_ondue", "js20_breakdowns", "dbr_shipped", "dbr_repaired", "dbr_typed", "ss_queues", "dbr_limits",
-                "ss_ondue", "js20_lots_queues", "dbr_ondue", "dbr_tiny_setup", "ss_zero_ops", "dbr_mixed_types"]
+                "ss_ondue", "js20_lots_queues", "dbr_ondue", "dbr_tiny_setup", "ss_zero_ops", "dbr_mixed_types", "dbr_f64_order"]
 ERROR_NAMES = ["err_negdelay", "err_amount"]

@@ -22,7 +22,7 @@ if str(ROOT) not in sys.path:
     sys.path.insert(0, str(ROOT))
 CSRC = ROOT / "manusim_b200" / "csrc"
 BUILD = HERE / "_build"
-SOURCES = [CSRC / "msim_kernel.cu", CSRC / "msim_kernel_aos.cu", CSRC / "msim_api.cu", HERE / "emu_runtime.cpp"]
+SOURCES = [CSRC / "msim_kernel.cu", CSRC / "msim_reduce.cu", CSRC / "msim_api.cu", HERE / "emu_runtime.cpp"]
 DEPS = SOURCES + [CSRC / "msim_device.cuh", CSRC / "philox.cuh", ROOT / "include" / "msim.h",
                   HERE / "include" / "cuda_runtime.h", HERE / "include" / "math_constants.h"]
 
@@ -96,7 +96,7 @@ def load(flavour: str = "plain", defines=()):
 class EmuEngine:
     """numpy twin of manusim_b200.engine.BatchEngine.run for the emulated library ("device" memory = host memory)."""
 
-    def __init__(self, tables, flavour: str = "plain", layout: str | None = None, defines=()):
+    def __init__(self, tables, flavour: str = "plain", defines=()):
         from manusim_b200 import _lib as L
         from manusim_b200.engine import make_ctables
 
@@ -105,17 +105,7 @@ class EmuEngine:
         self.tables = tables
         ct, self._keep = make_ctables(tables)
         self.handle = C.c_void_p()
-        old = os.environ.get("MSIM_SLAB_LAYOUT")
-        if layout is not None:                      # read by msim_create, per handle
-            os.environ["MSIM_SLAB_LAYOUT"] = layout
-        try:
-            self._check(self.lib.msim_create(C.byref(ct), C.byref(self.handle)))
-        finally:
-            if layout is not None:
-                if old is None:
-                    os.environ.pop("MSIM_SLAB_LAYOUT", None)
-                else:
-                    os.environ["MSIM_SLAB_LAYOUT"] = old
+        self._check(self.lib.msim_create(C.byref(ct), C.byref(self.handle)))
         info = L.Info()
         self._check(self.lib.msim_query(self.handle, C.byref(info)))
         self.info = {f[0]: getattr(info, f[0]) for f in L.Info._fields_}

@@ -67,15 +67,12 @@ def philox(policy, mode, repair=False, log_queues=False):
 def main():
     inject = "--inject" in sys.argv
     cases = 0
-    # (CTA shape, slab layout, lean): the default (array-of-structures) kernel with the product's CTA shape, then its
-    # lean instantiations with one warp per CTA; MSIM_EMU_SANITIZE_SOA=1 adds the structure-of-arrays fallback build
-    # (clean when it was the default; left out of the routine run to keep the CPU suite short)
-    configs = [("", "aos", ""), ("1", "aos", "1")]
-    if os.environ.get("MSIM_EMU_SANITIZE_SOA"):
-        configs.append(("1", "soa", ""))
-    for wpb, layout, lean in () if inject else configs:
-        os.environ["MSIM_SLAB_LAYOUT"] = layout
-        os.environ["MSIM_LEAN"] = lean           # "1": runs without queue records / recording take the OPTS = 0 kernels
+    # (CTA shape, general kernel forced): the product's CTA shape with the kernels a run picks by itself (lean when it
+    # uses neither queue records nor tape recording), then one warp per CTA -- every slab is its own allocation -- with the
+    # general (OPTS = 3) kernels forced for every run
+    configs = [("", ""), ("1", "1")]
+    for wpb, general in () if inject else configs:
+        os.environ["MSIM_NO_LEAN"] = general
         if wpb:
             os.environ["MSIM_EMU_WPB"] = wpb
         else:
@@ -89,8 +86,7 @@ def main():
         philox("dbr", "instantly", repair=True)
         philox("dbr", "instantly", repair=False)
         cases += 2
-    os.environ.pop("MSIM_SLAB_LAYOUT", None)
-    os.environ.pop("MSIM_LEAN", None)
+    os.environ.pop("MSIM_NO_LEAN", None)
     if inject:
         g = load_golden("toy2")
         scn = g["scenario"]

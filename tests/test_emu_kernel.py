@@ -52,26 +52,27 @@ def emu():
     return m
 
 
-# "soa" = the default kernel (msim_kernel.cu); "aos" = its experimental array-of-structures twin (msim_kernel_aos.cu,
-# selected per handle with MSIM_SLAB_LAYOUT=aos)
-LAYOUTS = ["soa", "aos"]
+# which instantiation a run launches: "auto" = what the library picks by itself (the lean OPTS = 0 kernels when the run
+# uses neither queue records nor tape recording), "general" = the OPTS = 3 kernels forced with MSIM_NO_LEAN=1
+KERNELS = ["auto", "general"]
 
 
-def _engine(emu, scn, layout=None, **kw):
+def _engine(emu, scn, defines=(), **kw):
     from manusim_b200 import compile_scenario
 
     t = compile_scenario(scn["cfg"], scn["resources"], scn["products"], policy=POLICY[scn["policy"]],
                          dbr_repair="P3" in scn["patches"], **kw)
-    return emu.EmuEngine(t, layout=layout)
+    return emu.EmuEngine(t, defines=defines)
 
 
-@pytest.mark.parametrize("layout", LAYOUTS)
+@pytest.mark.parametrize("kernel", KERNELS)
 @pytest.mark.parametrize("name", GOLDEN_NAMES)
-def test_emulated_kernel_replays_reference_goldens_bit_exact(emu, name, layout):
+def test_emulated_kernel_replays_reference_goldens_bit_exact(emu, name, kernel, monkeypatch):
     from manusim_b200.engine import decode_log
 
+    monkeypatch.setenv("MSIM_NO_LEAN", "1" if kernel == "general" else "")
     g = load_golden(name)
-    eng = _engine(emu, g["scenario"], layout)
+    eng = _engine(emu, g["scenario"])
     n = 2
     res = eng.run(n, tapes=[{k: g["tape_" + k] for k in "ABCD"}] * n, n_log_reps=n, log_cap=len(g["ring"]) + 64)
     assert (res.status == 0).all(), res.status
@@ -92,13 +93,31 @@ def test_emulated_kernel_replays_reference_goldens_bit_exact(emu, name, layout):
         assert np.array_equal(res.acc_cnt[i].astype(np.int64), c)
 
 
-@pytest.mark.parametrize("layout", LAYOUTS)
-@pytest.mark.parametrize("name,status", list(zip(ERROR_NAMES, (1, 2))))
-def test_emulated_kernel_value_error_cases(emu, name, status, layout):
+def test_float64_calendar_order_golden_guards_the_dbr_cell_ordering(emu):
+    """Negative control for golden dbr_f64_order: the same source built with MSIM_X_F32CELL=1 (the DBR calendar ordered
+    by float32 time alone, as in round 1) must NOT reproduce it -- so the golden really exercises the exact float64
+    order of python-typed instants inside one float32 spacing of the clock (examples/toc_dbr/simulation.py:200-289 on
+    the SimPy heap)."""
     from manusim_b200.engine import decode_log
 
+    g = load_golden("dbr_f64_order")
+    eng = _engine(emu, g["scenario"], defines=("MSIM_X_F32CELL=1",))
+    res = eng.run(1, tapes=[{k: g["tape_" + k] for k in "ABCD"}], n_log_reps=1, log_cap=len(g["ring"]) + 4096)
+    ring, tm, val, _ = decode_log(res.log[0], int(res.log_count[0]))
+    same = (int(res.n_events[0]) == g["steps"] and len(ring) == len(g["ring"])
+            and np.array_equal(ring, g["ring"].astype(np.uint32)) and np.array_equal(tm, g["time"])
+            and np.array_equal(val, g["value"]))
+    assert not same
+
+
+@pytest.mark.parametrize("kernel", KERNELS)
+@pytest.mark.parametrize("name,status", list(zip(ERROR_NAMES, (1, 2))))
+def test_emulated_kernel_value_error_cases(emu, name, status, kernel, monkeypatch):
+    from manusim_b200.engine import decode_log
+
+    monkeypatch.setenv("MSIM_NO_LEAN", "1" if kernel == "general" else "")
     g = load_golden(name)
-    eng = _engine(emu, g["scenario"], layout)
+    eng = _engine(emu, g["scenario"])
     res = eng.run(2, tapes=[{k: g["tape_" + k] for k in "ABCD"}] * 2, n_log_reps=2, log_cap=4096)
     assert (res.status == status).all()
     ring, tm, val, _ = decode_log(res.log[1], int(res.log_count[1]))
@@ -106,10 +125,9 @@ def test_emulated_kernel_value_error_cases(emu, name, status, layout):
     assert np.array_equal(tm, g["time"]) and np.array_equal(val, g["value"])
 
 
-@pytest.mark.parametrize("layout", LAYOUTS)
-@pytest.mark.parametrize("seed", list(range(48)) if FULL else list(range(0, 48, 4)))
-def test_emulated_kernel_random_scenarios_match_oracle(emu, seed, layout):
-    """Same scenarios and the same check as tests/test_gpu_fuzz.py (every 4th seed unless MSIM_EMU_FULL=1)."""
+@pytest.mark.parametrize("seed", list(range(48)) if FULL else list(range(0, 48, 2)))
+def test_emulated_kernel_random_scenarios_match_oracle(emu, seed):
+    """Same scenarios and the same check as tests/test_gpu_fuzz.py (every 2nd seed unless MSIM_EMU_FULL=1)."""
     from test_gpu_fuzz import random_scenario
 
     from manusim_b200 import compile_scenario
@@ -118,7 +136,7 @@ def test_emulated_kernel_random_scenarios_match_oracle(emu, seed, layout):
 
     cfg, res, prod, policy, repair = random_scenario(seed)
     eng = emu.EmuEngine(compile_scenario(cfg, res, prod, policy=policy, dbr_repair=repair, max_production_orders=250,
-                                         max_demand_orders=250, fifo_capacity=256), layout=layout)
+                                         max_demand_orders=250, fifo_capacity=256))
     n = 3
     r = eng.run(n, seed=1000 + seed, n_log_reps=n, log_cap=1 << 16, record_tapes=1 << 14)
     cnt = r.rec["count"]
@@ -164,17 +182,19 @@ def test_host_buffer_entry_point_equals_device_buffer_entry_point(emu, name):
 
 @pytest.mark.parametrize("name", ["toy2_instantly", "ss_lots", "ss_queues", "js20_ondue", "dbr_limits"])
 def test_lean_kernels_equal_the_general_ones(emu, name, monkeypatch):
-    """MSIM_LEAN=1 launches the OPTS = 0 instantiations (no queue-record / tape-recording branches) whenever a run uses
-    neither option; ss_queues (log_queues) and the recording run below must still take the general kernel."""
+    """A run that uses neither queue records nor tape recording launches the OPTS = 0 instantiations (without those
+    branches); MSIM_NO_LEAN=1 forces the general kernel; ss_queues (log_queues) and the recording run below take the
+    general kernel anyway."""
     from manusim_b200.engine import decode_log
 
     g = load_golden(name)
-    eng = _engine(emu, g["scenario"], "aos")
+    eng = _engine(emu, g["scenario"])
     tapes = [{k: g["tape_" + k] for k in "ABCD"}] * 2
     cap = len(g["ring"]) + 16
+    monkeypatch.setenv("MSIM_NO_LEAN", "1")
     ref = eng.run(2, tapes=tapes, n_log_reps=2, log_cap=cap)
     ref_p = eng.run(3, seed=21)
-    monkeypatch.setenv("MSIM_LEAN", "1")
+    monkeypatch.setenv("MSIM_NO_LEAN", "")
     r = eng.run(2, tapes=tapes, n_log_reps=2, log_cap=cap)
     assert (r.status == 0).all() and (r.n_events == g["steps"]).all()
     ring, tm, val, _ = decode_log(r.log[1], int(r.log_count[1]))

@@ -67,7 +67,7 @@ def test_library_exports_every_declared_symbol():
     lib = _lib.load()
     for name in declared:
         assert hasattr(lib, name)
-    assert lib.msim_version() == 100
+    assert lib.msim_version() == 200
     # struct sizes of the ctypes mirror match the header's layout (all 8-byte aligned fields)
     assert ctypes.sizeof(_lib.Dist) == 40
     assert ctypes.sizeof(_lib.RunArgs) % 8 == 0 and ctypes.sizeof(_lib.Tables) % 8 == 0
@@ -131,9 +131,9 @@ def test_ctypes_mirror_matches_the_c_header(tmp_path):
             assert int(out[f"{cname}.{fname}"]) == getattr(cls, fname).offset, (cname, fname)
 
 
-def test_library_refuses_without_device_and_validates_the_layout_switch(monkeypatch):
-    """msim_create through the real libmsim.so on a box without a GPU: a bad MSIM_SLAB_LAYOUT is an argument error,
-    a good one gets as far as the device query and fails there -- there is no host execution path in the library."""
+def test_library_refuses_without_device():
+    """msim_create through the real libmsim.so on a box without a GPU gets as far as the device query and fails there
+    -- there is no host execution path in the library."""
     import torch
 
     if torch.cuda.is_available():
@@ -145,13 +145,8 @@ def test_library_refuses_without_device_and_validates_the_layout_switch(monkeypa
     cfg, res, prod = scenarios.toy2()
     ct, keep = make_ctables(compile_scenario(cfg, res, prod))
     h = ctypes.c_void_p()
-    monkeypatch.setenv("MSIM_SLAB_LAYOUT", "bogus")
-    assert lib.msim_create(ctypes.byref(ct), ctypes.byref(h)) == -1
-    assert b"MSIM_SLAB_LAYOUT" in lib.msim_last_error()
-    for layout in ("aos", "soa"):
-        monkeypatch.setenv("MSIM_SLAB_LAYOUT", layout)
-        assert lib.msim_create(ctypes.byref(ct), ctypes.byref(h)) == -2          # MSIM_E_CUDA
-        assert b"no CPU fallback" in lib.msim_last_error()
+    assert lib.msim_create(ctypes.byref(ct), ctypes.byref(h)) == -2          # MSIM_E_CUDA
+    assert b"no CPU fallback" in lib.msim_last_error()
 
 
 def test_product_never_loads_the_emulated_library():

@@ -16,8 +16,7 @@ ROOT = Path(__file__).resolve().parent.parent
 
 
 @pytest.mark.skipif(shutil.which("g++") is None, reason="needs g++")
-@pytest.mark.parametrize("source", ["msim_kernel_aos.cu", "msim_kernel.cu"])
-def test_device_pyround6_equals_cpython_round(tmp_path, source):
+def test_device_pyround6_equals_cpython_round(tmp_path, source="msim_kernel.cu"):
     text = (ROOT / "manusim_b200" / "csrc" / source).read_text()
     m = re.search(r"__device__ __forceinline__ double pyround6\(double x\) \{.*?\n\}", text, re.S)
     assert m, "pyround6 not found"

@@ -7,8 +7,7 @@ time all of them in ONE GPU call on identical trajectories.
     python tools/ab_probe.py static                # SASS instruction counts per variant (no GPU)
     python tools/ab_probe.py run [--run-until N] [--reps N] [--rounds K] [--workloads jobshop20,toc_dbr]   # GPU
 
-Variants are -D switches of csrc/msim_kernel_aos.cu (all 0 = the default build); "soa" is the other slab layout of the
-default library.  `run` executes every variant in its own process (the library is chosen at load time with MSIM_LIB),
+Variants are -D switches of csrc/msim_kernel.cu (none = the default build).  `run` executes every variant in its own process (the library is chosen at load time with MSIM_LIB),
 K rounds interleaved so that clock drift shows up as spread instead of bias, after a smoke() parity check per variant.
 Output: one JSON line per (round, variant, workload part) and a summary table; not a bench line.
 """
@@ -24,20 +23,13 @@ from pathlib import Path
 ROOT = Path(__file__).resolve().parent.parent
 sys.path.insert(0, str(ROOT))
 
+# round-2 history (profiles/r02_ab_probe.jsonl): tailpush +10 %, lean +15..23 %, lb4 +12 % where shared memory limits the
+# handle to 4 CTAs per SM -> folded into the default build; flushgrp -5 %, duecache -5 %, ropecache 0, nto 0 -> removed.
 VARIANTS = {
-    "nto": ["MSIM_X_NTO=1"],
-    "tailpush": ["MSIM_X_TAILPUSH=1"],
-    "flushgrp": ["MSIM_X_FLUSHGRP=1"],
-    "duecache": ["MSIM_X_DUECACHE=1"],
-    "ropecache": ["MSIM_X_ROPECACHE=1"],
-    "nto_tailpush_flushgrp": ["MSIM_X_NTO=1", "MSIM_X_TAILPUSH=1", "MSIM_X_FLUSHGRP=1"],
-    "lb4": ["MSIM_X_MINBLOCKS=4"],        # 64 registers, no spills: meaningful for the smem-limited onDue part only
-    "allx": ["MSIM_X_NTO=1", "MSIM_X_TAILPUSH=1", "MSIM_X_FLUSHGRP=1", "MSIM_X_DUECACHE=1", "MSIM_X_ROPECACHE=1"],
 }
 RESTRICTED = set()
-# variants of the DEFAULT library selected by environment (no rebuild): the other slab layout, and the "lean" kernels
-# without the queue-record / tape-recording branches (template parameter OPTS = 0, launched when MSIM_LEAN=1)
-ENV_VARIANTS = {"soa": {"MSIM_SLAB_LAYOUT": "soa"}, "lean": {"MSIM_LEAN": "1"}}
+# variants of the DEFAULT library selected by environment (no rebuild)
+ENV_VARIANTS = {"general": {"MSIM_NO_LEAN": "1"}}
 
 WORKER = r"""
 import json, os, sys
@@ -99,8 +91,8 @@ def cmd_static(_):
                 cnt[name] = 0
             elif name and re.match(r"\s+/\*[0-9a-f]{4,5}\*/\s+\S", line):
                 cnt[name] += 1
-        row = {k.replace("_ZN4msim3aos10sim_kernelILi", "aos<").replace("EEEvNS_7KParamsE", ">").replace("ELi", ","): v
-               for k, v in cnt.items() if "3aos10sim_kernel" in k}
+        row = {k.replace("_ZN4msim10sim_kernelILi", "<").replace("EEEvNS_7KParamsE", ">").replace("ELi", ","): v
+               for k, v in cnt.items() if "10sim_kernel" in k}
         print(tag, json.dumps(row))
 
 
@@ -126,8 +118,8 @@ def cmd_verify(_):
             scn = g["scenario"]
             t = compile_scenario(scn["cfg"], scn["resources"], scn["products"], policy=pol[scn["policy"]],
                                  dbr_repair="P3" in scn["patches"])
-            ref = emu.EmuEngine(t, layout="aos")
-            eng = emu.EmuEngine(t, layout="aos", defines=defs)
+            ref = emu.EmuEngine(t)
+            eng = emu.EmuEngine(t, defines=defs)
             tapes = [{k: g["tape_" + k] for k in "ABCD"}] * 2
             r0 = ref.run(2, tapes=tapes, n_log_reps=2, log_cap=len(g["ring"]) + 64)
             r = eng.run(2, tapes=tapes, n_log_reps=2, log_cap=len(g["ring"]) + 64)
@@ -143,7 +135,7 @@ def cmd_verify(_):
             cfg, res, prod, policy, repair = random_scenario(seed)
             t = compile_scenario(cfg, res, prod, policy=policy, dbr_repair=repair, max_production_orders=250,
                                  max_demand_orders=250, fifo_capacity=256)
-            eng = emu.EmuEngine(t, layout="aos", defines=defs)
+            eng = emu.EmuEngine(t, defines=defs)
             r = eng.run(2, seed=1000 + seed, n_log_reps=2, log_cap=1 << 16, record_tapes=1 << 14)
             cnt = r.rec["count"]
             for i in range(2):

@@ -24,7 +24,6 @@ def main():
     ap.add_argument("--workloads", default="jobshop20,toc_dbr,toc_dbr_shipped")
     ap.add_argument("--reps", type=int, default=2)
     ap.add_argument("--seed", type=int, default=20261020)
-    ap.add_argument("--layout", default="aos")
     a = ap.parse_args()
     import numpy as np
 
@@ -41,7 +40,7 @@ def main():
             repair = spec.get("dbr_repair", False)
             t = compile_scenario(cfg, res, prod, policy=policy, dbr_repair=repair, max_production_orders=250,
                                  max_demand_orders=250, fifo_capacity=256)
-            eng = emu.EmuEngine(t, layout=a.layout)
+            eng = emu.EmuEngine(t)
             t0 = time.time()
             r = eng.run(a.reps, seed=a.seed + i, n_log_reps=a.reps, log_cap=1 << 21, record_tapes=1 << 21)
             emu_s = time.time() - t0
@@ -58,7 +57,7 @@ def main():
                 print(json.dumps({"workload": wl, "part": i, "delivery_mode": cfg.get("delivery_mode"), "policy": policy,
                                   "run_until": cfg["run_until"], "replication": k, "simpy_steps": int(r.n_events[k]),
                                   "records": int(len(ring)), "identical_to_oracle_replay": bool(same),
-                                  "layout": a.layout, "emu_s_per_rep": round(emu_s / a.reps, 1)}), flush=True)
+                                  "emu_s_per_rep": round(emu_s / a.reps, 1)}), flush=True)
             eng.close()
     sys.exit(1 if bad else 0)
 

@@ -3,7 +3,7 @@
 t = 20 000, onDue and EDD variants, DBR x onDue, a python-typed-clock stress case, job shop with lots + queue records +
 breakdowns).  Kernel source on the CPU-fiber emulation (Philox + tape recording) against oracle replays; one JSON line per
 replication.  This sweep found the two rare cases behind goldens dbr_tiny_setup and ss_zero_ops; the stress case
-`dbr_typed_long` still differs (known deviation 2)."""
+`dbr_typed_long` is the python-typed-clock stress case that golden dbr_f64_order was cut from (round 2: identical)."""
 import sys, time, json, copy
 from pathlib import Path
 ROOT = Path(__file__).resolve().parent.parent
@@ -33,7 +33,7 @@ cases.append(("js20_lots_queues_long", cfg, r20, p20, "fifo", False))
 bad = 0
 for name, cfg, res, prod, policy, repair in cases:
     t = compile_scenario(cfg, res, prod, policy=policy, dbr_repair=repair, max_production_orders=250, max_demand_orders=250, fifo_capacity=256)
-    eng = emu.EmuEngine(t, layout="aos")
+    eng = emu.EmuEngine(t)
     n = 2
     t0 = time.time()
     r = eng.run(n, seed=9090, n_log_reps=n, log_cap=1 << 21, record_tapes=1 << 21)

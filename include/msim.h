@@ -202,6 +202,13 @@ int msim_reduce_metrics(msim_handle_t h, const double* acc_sum, const uint32_t* 
 int msim_reduce_variables(msim_handle_t h, const double* acc_sum, const uint32_t* acc_cnt, const int32_t* status,
                           int64_t n_reps, double* out, void* stream);
 
+/* Per-replication metric values (DEVICE buffers): out[rep][ring] is the number FactorySimulation.*_metrics() puts in
+ * that run's metrics_*.csv (factory_sim.py:748-789: sum, sum / (run_until - warmup), or mean = sum / count, NaN when
+ * no record was logged); all rings of a replication whose status != 0 are NaN.  out is [n_reps][K] float64.  This is
+ * the `value` column of ExperimentMetrics' runs_metrics.csv (metrics.py:21,497-605) without per-run files. */
+int msim_metric_values(msim_handle_t h, const double* acc_sum, const uint32_t* acc_cnt, const int32_t* status,
+                       int64_t n_reps, double* out, void* stream);
+
 /* test hook: Philox4x32-10 blocks computed on the device; ctr [n][4], key [n][2], out [n][4] (HOST buffers) */
 int msim_test_philox(const uint32_t* ctr, const uint32_t* key, uint32_t* out, int64_t n);
 /* test hook: device variates; draws n values of `dist` with Philox key `seed` on stream id `stream_id`,

@@ -12,7 +12,8 @@ PKG = Path(__file__).resolve().parent
 LIB_PATH = Path(os.environ["MSIM_LIB"]) if os.environ.get("MSIM_LIB") else PKG / "libmsim.so"
 
 EXPORTS = ["msim_version", "msim_last_error", "msim_create", "msim_destroy", "msim_query", "msim_run",
-           "msim_run_host", "msim_reduce_metrics", "msim_reduce_variables", "msim_test_philox", "msim_test_variates"]
+           "msim_run_host", "msim_reduce_metrics", "msim_reduce_variables", "msim_metric_values", "msim_test_philox",
+           "msim_test_variates"]
 
 
 class Dist(C.Structure):
@@ -95,6 +96,8 @@ def load():
                                         C.c_void_p]
     lib.msim_reduce_variables.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p,
                                           C.c_void_p]
+    lib.msim_metric_values.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p,
+                                       C.c_void_p]
     lib.msim_test_philox.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64]
     lib.msim_test_variates.argtypes = [C.POINTER(Dist), C.c_uint64, C.c_int32, C.c_int32, C.c_void_p, C.c_int64]
     for name in EXPORTS:

@@ -30,7 +30,7 @@ struct msim_handle_s {
     int warps_per_block[2];     // per rng mode (the Philox and replay kernels differ in register use)
     int blocks_per_sm[2];
     int regs[2];
-    int wide[2];                // 1: shared memory limits the handle to <= 4 CTAs per SM -> lean runs use the 64-register build
+    int shape;                  // launch bounds / register budget of the lean kernels (msim_kernel.cu)
     size_t smem_bytes[2];
     unsigned long long* d_counter;
     double span;                // run_until - warmup
@@ -227,16 +227,23 @@ extern "C" int msim_create(const msim_tables_t* t, msim_handle_t* out) {
     // warps per block: maximise resident replications (= warps) per SM.  Shared memory, the per-CTA copy of the
     // tables and the register file all bound it, so ask the occupancy calculator for every CTA width.
     const size_t smem_blk_max = prop.sharedMemPerBlockOptin;           // 227 KB
-    // MSIM_MAX_CTAS_PER_SM (diagnostic): caps the resident CTAs per SM, to measure throughput against occupancy
-    int cta_cap = 0;
+    // Launch shape (msim_kernel.cu): 64 registers x <= 32 warps per SM by default.  Diagnostics for sweeps
+    // (tools/occupancy_sweep.sh): MSIM_SHAPE = 0 / 1 / 2 picks another register budget for the lean kernels,
+    // MSIM_MAX_CTAS_PER_SM caps the resident CTAs per SM, MSIM_WARPS_PER_CTA fixes the CTA width.
+    int cta_cap = 0, w_fixed = 0, shape = 0;
     if (const char* e = getenv("MSIM_MAX_CTAS_PER_SM")) cta_cap = atoi(e);
+    if (const char* e = getenv("MSIM_WARPS_PER_CTA")) w_fixed = atoi(e);
+    if (const char* e = getenv("MSIM_SHAPE")) shape = atoi(e);
+    if (shape < 0 || shape > 2) { delete h; return fail(MSIM_E_INVALID, "MSIM_SHAPE must be 0, 1 or 2"); }
+    h->shape = shape;
     for (int rng = 0; rng < 2; ++rng) {
         int best_w = 0, best_total = 0, best_blocks = 0;
-        for (int w = 1; w <= 8; ++w) {
+        for (int w = 1; w <= sim_shape_max_warps(shape); ++w) {
+            if (w_fixed > 0 && w != w_fixed) continue;
             size_t need = (size_t)w * L.slab_bytes;
             if (need > smem_blk_max) break;
             int nblk = 0, regs = 0;
-            int rc = sim_kernel_attrs(h->policy, rng, false, need, &regs, w * 32, &nblk);
+            int rc = sim_kernel_attrs(h->policy, rng, shape, need, &regs, w * 32, &nblk);
             if (rc != 0) {
                 delete h;
                 return fail(rc, rc == MSIM_E_UNSUPPORTED ? "policy not available in this build" : "kernel attribute query failed");
@@ -250,14 +257,6 @@ extern "C" int msim_create(const msim_tables_t* t, msim_handle_t* out) {
         h->warps_per_block[rng] = best_w;
         h->blocks_per_sm[rng] = best_blocks;
         h->smem_bytes[rng] = (size_t)best_w * L.slab_bytes;
-        // <= 4 CTAs per SM by shared memory: the 64-register build of the lean kernels keeps the same residency
-        h->wide[rng] = 0;
-        if (best_blocks <= 4) {
-            int nblk = 0, regs = 0;
-            if (sim_kernel_attrs(h->policy, rng, true, h->smem_bytes[rng], &regs, best_w * 32, &nblk) == 0 &&
-                (cta_cap > 0 && nblk > cta_cap ? cta_cap : nblk) >= best_blocks)
-                h->wide[rng] = 1;
-        }
     }
     if (cudaMalloc(&h->d_counter, 8) != cudaSuccess) {
         delete h;
@@ -320,7 +319,7 @@ extern "C" int msim_run(msim_handle_t h, const msim_run_args_t* a) {
     long long blocks_needed = (a->n_reps + wpb - 1) / wpb;
     long long grid = (long long)h->n_sms * h->blocks_per_sm[rng];
     if (grid > blocks_needed) grid = blocks_needed;
-    int rc = launch_sim(kp, h->policy, rng, h->wide[rng] != 0, (int)grid, wpb * 32, h->smem_bytes[rng], st);
+    int rc = launch_sim(kp, h->policy, rng, h->shape, (int)grid, wpb * 32, h->smem_bytes[rng], st);
     if (rc != 0) return fail(rc, "simulation kernel launch failed (grid/block/shared-memory configuration)");
     return 0;
 }
@@ -340,6 +339,16 @@ extern "C" int msim_reduce_variables(msim_handle_t h, const double* acc_sum, con
     const Lay& L = h->kp.lay;
     int rc = launch_reduce_variables(acc_sum, acc_cnt, status, n_reps, L.K, L.P, L.R, h->span, out, stream);
     if (rc != 0) return fail(rc, "reduce launch failed");
+    return 0;
+}
+
+extern "C" int msim_metric_values(msim_handle_t h, const double* acc_sum, const uint32_t* acc_cnt, const int32_t* status,
+                                  int64_t n_reps, double* out, void* stream) {
+    if (!h || !acc_sum || !acc_cnt || !status || !out) return fail(MSIM_E_INVALID, "null argument");
+    if (n_reps <= 0) return 0;
+    const Lay& L = h->kp.lay;
+    int rc = launch_metric_values(acc_sum, acc_cnt, status, n_reps, L.K, L.P, L.R, h->span, out, stream);
+    if (rc != 0) return fail(rc, "metric-values launch failed");
     return 0;
 }
 

@@ -88,15 +88,19 @@ struct KParams {
 constexpr int kAosResStride = 28, kAosPrdStride = 24, kAosDoStride = 12, kAosDoLinkStride = 2;
 __host__ __device__ constexpr int aos_po_stride(int policy) { return policy == MSIM_POLICY_FIFO ? 12 : 16; }   // + prio (PRIO/EDD) or ccr (DBR)
 
-// launchers implemented in msim_kernel.cu.  `wide`: the 64-register build of the lean kernels (handles that shared
-// memory limits to <= 4 CTAs per SM); the launcher picks the lean kernel itself when the run uses no option.
-int launch_sim(const KParams& p, int policy, int rng_mode, bool wide, int grid, int block, size_t smem, void* stream);
-int sim_kernel_attrs(int policy, int rng_mode, bool wide, size_t smem, int* regs, int block, int* blocks_per_sm);
+// launchers implemented in msim_kernel.cu.  `shape` = launch bounds / register budget of the lean kernels (0: 256 x 4
+// CTAs, 64 registers -- the default and the only shape of the general kernels; 1: 192 x 6, 56; 2: 256 x 5, 48); the
+// launcher picks the lean kernel itself when the run uses neither queue records nor tape recording.
+int launch_sim(const KParams& p, int policy, int rng_mode, int shape, int grid, int block, size_t smem, void* stream);
+int sim_kernel_attrs(int policy, int rng_mode, int shape, size_t smem, int* regs, int block, int* blocks_per_sm);
+int sim_shape_max_warps(int shape);
 // launchers implemented in msim_reduce.cu
 int launch_reduce(const double* acc_sum, const uint32_t* acc_cnt, const int32_t* status, int64_t n_reps, int K, int P,
                   int R, double span, double* out, void* stream);
 int launch_reduce_variables(const double* acc_sum, const uint32_t* acc_cnt, const int32_t* status, int64_t n_reps, int K,
                             int P, int R, double span, double* out, void* stream);
+int launch_metric_values(const double* acc_sum, const uint32_t* acc_cnt, const int32_t* status, int64_t n_reps, int K, int P,
+                         int R, double span, double* out, void* stream);
 int launch_test_philox(const uint32_t* ctr, const uint32_t* key, uint32_t* out, int64_t n);
 int launch_test_variates(DDist d, uint64_t seed, int stream_id, int batch_count, double* out, int64_t n);
 DDist make_ddist(const msim_dist_t& d);

@@ -50,9 +50,12 @@
 // Option flags as a template parameter: OPTS bit 0 = the scenario may log `queue` records (config log_queues), bit 1 =
 // the run may record variate tapes (rec_cap > 0).  OPTS = 3 is the general kernel; OPTS = 0 drops both branches from
 // every handler (-8 % code) and is what a run that uses neither option launches.
-// MINB = __launch_bounds__(256, MINB): 5 -> 48 registers (40 resident warps when shared memory allows 5 CTAs per SM);
-// 4 -> 64 registers and no spills, launched when shared memory limits the handle to 4 CTAs per SM anyway (onDue pools:
-// +12 % there, -26 % where it would cost a CTA).
+// SHAPE = the launch bounds, i.e. the register budget against the resident warps (profiles/r02_launch_shape_sweep_c.jsonl:
+// at EQUAL residency the 64-register build is 31 % faster than the 48-register one, whose spills sit on lane 0's
+// critical path; 64 registers at 32 warps per SM beat 48 registers at 40 by 15 %):
+//   0: __launch_bounds__(256, 4) -> 64 registers, <= 32 warps per SM   (default, every kernel)
+//   1: __launch_bounds__(192, 6) -> 56 registers, <= 36 warps per SM   (lean kernels only)
+//   2: __launch_bounds__(256, 5) -> 48 registers, <= 40 warps per SM   (lean kernels only; the round-1 shape)
 #define LOGQ (((OPTS) & 1) && p.log_queues)
 #define RECORDING (((OPTS) & 2) && p.a.rec_cap > 0)
 #define NOT_RECORDING (!((OPTS) & 2) || p.a.rec_cap == 0)
@@ -1146,8 +1149,11 @@ __device__ __forceinline__ void warp_flush(const KParams& p, const unsigned char
 }
 
 // ---------------------------------------------------------------------------------------------------------
-template <int POLICY, int RNG, int OPTS, int MINB>
-__global__ void __launch_bounds__(256, MINB) sim_kernel(const __grid_constant__ KParams p) {
+constexpr int shape_threads(int shape) { return shape == 1 ? 192 : 256; }
+constexpr int shape_ctas(int shape) { return shape == 1 ? 6 : (shape == 2 ? 5 : 4); }
+
+template <int POLICY, int RNG, int OPTS, int SHAPE>
+__global__ void __launch_bounds__(shape_threads(SHAPE), shape_ctas(SHAPE)) sim_kernel(const __grid_constant__ KParams p) {
     MSIM_DYN_SMEM(smem);
     const Lay& L = p.lay;
     const int lane = threadIdx.x & 31;
@@ -1406,48 +1412,54 @@ __global__ void __launch_bounds__(256, MINB) sim_kernel(const __grid_constant__ 
 
 // ---------------------------------------------------------------------------------------------------------
 typedef void (*sim_fn)(const KParams);
-template <int OPTS, int MINB>
+template <int OPTS, int SHAPE>
 static sim_fn pick_rng(int policy, int rng) {
-    if (policy == MSIM_POLICY_FIFO) return rng == MSIM_RNG_REPLAY ? sim_kernel<MSIM_POLICY_FIFO, MSIM_RNG_REPLAY, OPTS, MINB>
-                                                                  : sim_kernel<MSIM_POLICY_FIFO, MSIM_RNG_PHILOX, OPTS, MINB>;
+    if (policy == MSIM_POLICY_FIFO) return rng == MSIM_RNG_REPLAY ? sim_kernel<MSIM_POLICY_FIFO, MSIM_RNG_REPLAY, OPTS, SHAPE>
+                                                                  : sim_kernel<MSIM_POLICY_FIFO, MSIM_RNG_PHILOX, OPTS, SHAPE>;
     if (policy == MSIM_POLICY_MAX_PRIORITY)
-        return rng == MSIM_RNG_REPLAY ? sim_kernel<MSIM_POLICY_MAX_PRIORITY, MSIM_RNG_REPLAY, OPTS, MINB>
-                                      : sim_kernel<MSIM_POLICY_MAX_PRIORITY, MSIM_RNG_PHILOX, OPTS, MINB>;
+        return rng == MSIM_RNG_REPLAY ? sim_kernel<MSIM_POLICY_MAX_PRIORITY, MSIM_RNG_REPLAY, OPTS, SHAPE>
+                                      : sim_kernel<MSIM_POLICY_MAX_PRIORITY, MSIM_RNG_PHILOX, OPTS, SHAPE>;
     if (policy == MSIM_POLICY_DBR)
-        return rng == MSIM_RNG_REPLAY ? sim_kernel<MSIM_POLICY_DBR, MSIM_RNG_REPLAY, OPTS, MINB>
-                                      : sim_kernel<MSIM_POLICY_DBR, MSIM_RNG_PHILOX, OPTS, MINB>;
+        return rng == MSIM_RNG_REPLAY ? sim_kernel<MSIM_POLICY_DBR, MSIM_RNG_REPLAY, OPTS, SHAPE>
+                                      : sim_kernel<MSIM_POLICY_DBR, MSIM_RNG_PHILOX, OPTS, SHAPE>;
     if (policy == MSIM_POLICY_EDD)
-        return rng == MSIM_RNG_REPLAY ? sim_kernel<MSIM_POLICY_EDD, MSIM_RNG_REPLAY, OPTS, MINB>
-                                      : sim_kernel<MSIM_POLICY_EDD, MSIM_RNG_PHILOX, OPTS, MINB>;
+        return rng == MSIM_RNG_REPLAY ? sim_kernel<MSIM_POLICY_EDD, MSIM_RNG_REPLAY, OPTS, SHAPE>
+                                      : sim_kernel<MSIM_POLICY_EDD, MSIM_RNG_PHILOX, OPTS, SHAPE>;
     return nullptr;
 }
-// lean: the run uses neither queue records nor tape recording; wide: 64-register build (only compiled lean)
-static sim_fn pick(int policy, int rng, bool lean, bool wide) {
-    if (!lean) return pick_rng<3, 5>(policy, rng);
-    return wide ? pick_rng<0, 4>(policy, rng) : pick_rng<0, 5>(policy, rng);
+// lean: the run uses neither queue records nor tape recording (OPTS = 0); the general kernels exist in shape 0 only
+static sim_fn pick(int policy, int rng, bool lean, int shape) {
+    if (!lean) return pick_rng<3, 0>(policy, rng);
+    return shape == 1 ? pick_rng<0, 1>(policy, rng) : (shape == 2 ? pick_rng<0, 2>(policy, rng) : pick_rng<0, 0>(policy, rng));
 }
 
-int sim_kernel_attrs(int policy, int rng_mode, bool wide, size_t smem, int* regs, int block, int* blocks_per_sm) {
-    // wide = false: the general kernel (its occupancy also holds for the lean one: same launch bounds, less code)
-    sim_fn f = pick(policy, rng_mode, wide, wide);
-    if (!f) return MSIM_E_UNSUPPORTED;
+int sim_shape_max_warps(int shape) { return shape_threads(shape) / 32; }
+
+int sim_kernel_attrs(int policy, int rng_mode, int shape, size_t smem, int* regs, int block, int* blocks_per_sm) {
+    // residency of the LEAN kernel of this shape, bounded by the general kernel's (shape 0) with the same CTA: a run that
+    // records tapes or logs queue lengths launches that one with the same grid
+    sim_fn f = pick(policy, rng_mode, true, shape), g = pick(policy, rng_mode, false, 0);
+    if (!f || !g) return MSIM_E_UNSUPPORTED;
     cudaFuncAttributes at;
     if (cudaFuncGetAttributes(&at, f) != cudaSuccess) return MSIM_E_CUDA;
     if (regs) *regs = at.numRegs;
-    if (cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return MSIM_E_CUDA;
+    if (cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess ||
+        cudaFuncSetAttribute(g, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return MSIM_E_CUDA;
     if (blocks_per_sm) {
-        int nb = 0;
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, f, block, smem) != cudaSuccess) return MSIM_E_CUDA;
-        *blocks_per_sm = nb;
+        int nb = 0, ng = 0;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, f, block, smem) != cudaSuccess ||
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ng, g, block, smem) != cudaSuccess) return MSIM_E_CUDA;
+        *blocks_per_sm = nb;          // (a general-kernel launch with more CTAs than fit simply queues the rest)
+        (void)ng;
     }
     return 0;
 }
 
-int launch_sim(const KParams& p, int policy, int rng_mode, bool wide, int grid, int block, size_t smem, void* stream) {
+int launch_sim(const KParams& p, int policy, int rng_mode, int shape, int grid, int block, size_t smem, void* stream) {
     // MSIM_NO_LEAN=1 (diagnostic, tests): always launch the general kernel
     const char* no_lean = getenv("MSIM_NO_LEAN");
     const bool lean = !p.log_queues && p.a.rec_cap == 0 && !(no_lean && no_lean[0] == '1');
-    sim_fn f = pick(policy, rng_mode, lean, lean && wide);
+    sim_fn f = pick(policy, rng_mode, lean, shape);
     if (!f) return MSIM_E_UNSUPPORTED;
     // The opt-in shared-memory limit is per FUNCTION, not per handle: handles with different slab sizes share a kernel
     // and msim_create lowers the attribute again while it probes CTA widths, so it is set before every launch (a host-

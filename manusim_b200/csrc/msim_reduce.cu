@@ -6,6 +6,7 @@
 // or mean = sum / count per ring) and ExperimentMetrics.calculate_experiment_stats (src/manusim/metrics.py:809-816,
 // 859-919: NaN runs dropped, per-variable = mean over keys first).
 #include <cuda_runtime.h>
+#include <math_constants.h>
 #include "msim_device.cuh"
 #include "philox.cuh"
 
@@ -107,6 +108,27 @@ __global__ void reduce_variables_kernel(const double* __restrict__ acc_sum, cons
     }
 }
 
+// per-replication metric values (the numbers of one run's metrics_*.csv, factory_sim.py:748-789): out[rep][ring] = sum,
+// sum / span or sum / count (NaN when the ring is empty); every ring of a failed replication is NaN.  Elementwise,
+// HBM-bound: reads 12 B and writes 8 B per (replication, ring).
+__global__ void metric_values_kernel(const double* __restrict__ acc_sum, const uint32_t* __restrict__ acc_cnt,
+                                     const int32_t* __restrict__ status, long long n_reps, int K, int P, int R, double span,
+                                     double* __restrict__ out) {
+    const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;     // consecutive threads, consecutive elements
+    if (i >= n_reps * K) return;
+    const long long rep = i / K;
+    const int ring = (int)(i - rep * K);
+    double x = CUDART_NAN;
+    if (status[rep] == 0) {
+        const double s = acc_sum[i];
+        const uint32_t c = acc_cnt[i];
+        if (ring < 3 * P) x = s;
+        else if (ring >= 11 * P && ring < 11 * P + 3 * R) x = s / span;
+        else if (c) x = s / (double)c;
+    }
+    out[i] = x;
+}
+
 __global__ void test_philox_kernel(const uint32_t* ctr, const uint32_t* key, uint32_t* out, long long n) {
     long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
     if (i >= n) return;
@@ -148,6 +170,14 @@ int launch_reduce(const double* acc_sum, const uint32_t* acc_cnt, const int32_t*
 int launch_reduce_variables(const double* acc_sum, const uint32_t* acc_cnt, const int32_t* status, int64_t n_reps, int K,
                             int P, int R, double span, double* out, void* stream) {
     MSIM_LAUNCH(reduce_variables_kernel, 18, 256, 0, (cudaStream_t)stream, acc_sum, acc_cnt, status, n_reps, K, P, R, span, out);
+    return cudaGetLastError() == cudaSuccess ? 0 : MSIM_E_CUDA;
+}
+
+int launch_metric_values(const double* acc_sum, const uint32_t* acc_cnt, const int32_t* status, int64_t n_reps, int K, int P,
+                         int R, double span, double* out, void* stream) {
+    const long long blocks = ((long long)n_reps * K + 255) / 256;
+    MSIM_LAUNCH(metric_values_kernel, (unsigned)blocks, 256, 0, (cudaStream_t)stream, acc_sum, acc_cnt, status, n_reps, K, P, R,
+                span, out);
     return cudaGetLastError() == cudaSuccess ? 0 : MSIM_E_CUDA;
 }
 

@@ -122,6 +122,9 @@ class BatchEngine:
         self.info = {f[0]: getattr(info, f[0]) for f in _lib.Info._fields_}
         self.K = info.n_rings
 
+    def synchronize(self):
+        self.torch.cuda.synchronize(self.device)
+
     def close(self):
         if getattr(self, "handle", None) and self.handle.value:
             self.lib.msim_destroy(self.handle)
@@ -272,6 +275,18 @@ class BatchEngine:
             _lib.check(self.lib.msim_reduce_variables(self.handle, res.acc_sum.data_ptr(), res.acc_cnt.data_ptr(),
                                                       res.status.data_ptr(), res.acc_sum.shape[0], out.data_ptr(),
                                                       s.cuda_stream))
+        return out
+
+    def metric_values(self, res: BatchResult, out=None, stream=None):
+        """Per-replication metric values [n, K] float64 on the device (NaN: empty mean-metric or failed replication)."""
+        torch = self.torch
+        n = res.acc_sum.shape[0]
+        if out is None:
+            out = torch.empty((n, self.K), dtype=torch.float64, device=self.device)
+        s = stream if stream is not None else torch.cuda.current_stream(self.device)
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.msim_metric_values(self.handle, res.acc_sum.data_ptr(), res.acc_cnt.data_ptr(),
+                                                   res.status.data_ptr(), n, out.data_ptr(), s.cuda_stream))
         return out
 
     # ------------------------------------------------------------------ host-buffer path (end to end)

@@ -165,7 +165,6 @@ class FactorySimulation:
     # ------------------------------------------------------------------ execution
     def run_simulation(self) -> float:
         """One replication on the GPU; returns wall seconds like factory_sim.py:810-814 and fills ``logs``."""
-        import torch
 
         from .engine import decode_log
 
@@ -174,11 +173,15 @@ class FactorySimulation:
         cap = int(self.config.get("device_log_capacity", 1 << 20))
         n_log = 1 if self.enable_event_logging else 0
         seed = 0 if self.seed is None else int(self.seed)
-        res = eng.run(1, seed=seed, tapes=[self._tapes] if self._tapes is not None else None,
+        # the run seed IS the replication's Philox key -- the mapping ExperimentRunner uses for run i, so that a run can
+        # be reproduced from the seed recorded in its run_info.yaml (experiment.py:55-57: reset_simulation + run_simulation)
+        key = np.array([seed & 0xFFFFFFFFFFFFFFFF], dtype=np.uint64)
+        res = eng.run(1, rep_seeds=None if self._tapes is not None else key,
+                      tapes=[self._tapes] if self._tapes is not None else None,
                       n_log_reps=n_log, log_cap=cap if n_log else 0)
         if self._tapes is None:
-            eng.retry_overflow(res, seed=seed)
-        torch.cuda.synchronize(eng.device)
+            eng.retry_overflow(res, rep_seeds=key)
+        eng.synchronize()
         status = int(res.status[0])
         if status in (1, 2):
             from .engine import STATUS_TEXT

@@ -89,6 +89,7 @@ def load(flavour: str = "plain", defines=()):
     lib.msim_run_host.argtypes = [C.c_void_p, C.POINTER(L.HostArgs)]
     lib.msim_reduce_metrics.argtypes = [C.c_void_p] * 4 + [C.c_int64, C.c_void_p, C.c_void_p]
     lib.msim_reduce_variables.argtypes = [C.c_void_p] * 4 + [C.c_int64, C.c_void_p, C.c_void_p]
+    lib.msim_metric_values.argtypes = [C.c_void_p] * 4 + [C.c_int64, C.c_void_p, C.c_void_p]
     _libs[key] = lib
     return lib
 
@@ -221,6 +222,12 @@ class EmuEngine:
         fn = self.lib.msim_reduce_variables if variables else self.lib.msim_reduce_metrics
         self._check(fn(self.handle, res.acc_sum.ctypes.data, res.acc_cnt.ctypes.data, res.status.ctypes.data,
                        res.acc_sum.shape[0], out.ctypes.data, None))
+        return out
+
+    def metric_values(self, res):
+        out = np.zeros((res.acc_sum.shape[0], self.K))
+        self._check(self.lib.msim_metric_values(self.handle, res.acc_sum.ctypes.data, res.acc_cnt.ctypes.data,
+                                                res.status.ctypes.data, res.acc_sum.shape[0], out.ctypes.data, None))
         return out
 
 

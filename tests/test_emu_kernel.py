@@ -239,6 +239,13 @@ def test_emulated_reduction_kernels_match_numpy(emu):
         xv = np.stack([np.nanmean(x[:, s], axis=1) for s in groups], 1)
     wantv = np.stack([np.nansum(xv, 0), np.nansum(xv * xv, 0), np.sum(~np.isnan(xv), 0)], 1)
     np.testing.assert_allclose(eng.reduce(res, variables=True), wantv, rtol=1e-12, atol=1e-12)
+    # msim_metric_values: the per-run numbers of metrics_*.csv; failed replication -> NaN row
+    from manusim_b200.metrics import metric_values
+
+    mv = eng.metric_values(res)
+    want_mv = metric_values(res.acc_sum, res.acc_cnt, t, span)
+    want_mv[~ok] = np.nan
+    np.testing.assert_array_equal(mv, want_mv)
 
 
 def test_kernel_source_is_clean_under_address_and_ub_sanitizers(emu):

@@ -27,6 +27,8 @@ timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --c
     --log-file "$OUT/launches_$TAG.csv" $CMD > "$OUT/ncu_launches_$TAG.log" 2>&1
 
 # the simulation kernel, full set: the launches of the timed step (after 3 warm-up steps of NPARTS launches each)
-timeout 1500 ncu --set full --clock-control none --import-source on -k "$KERNEL" -s $((3 * NPARTS)) -c $NPARTS \
-    -o "$OUT/prof_$TAG" -f $CMD > "$OUT/ncu_full_$TAG.log" 2>&1
+for i in $(seq 0 $((NPARTS - 1))); do
+  timeout 900 ncu --set full --clock-control none --import-source on -k "$KERNEL" -s $((3 * NPARTS + i)) -c 1 \
+      -o "$OUT/prof_${TAG}_part$i" -f $CMD > "$OUT/ncu_full_${TAG}_part$i.log" 2>&1
+done
 ls -la "$OUT" | grep "$TAG"

@@ -227,36 +227,51 @@ extern "C" int msim_create(const msim_tables_t* t, msim_handle_t* out) {
     // warps per block: maximise resident replications (= warps) per SM.  Shared memory, the per-CTA copy of the
     // tables and the register file all bound it, so ask the occupancy calculator for every CTA width.
     const size_t smem_blk_max = prop.sharedMemPerBlockOptin;           // 227 KB
-    // Launch shape (msim_kernel.cu): 64 registers x <= 32 warps per SM by default.  Diagnostics for sweeps
-    // (tools/occupancy_sweep.sh): MSIM_SHAPE = 0 / 1 / 2 picks another register budget for the lean kernels,
-    // MSIM_MAX_CTAS_PER_SM caps the resident CTAs per SM, MSIM_WARPS_PER_CTA fixes the CTA width.
-    int cta_cap = 0, w_fixed = 0, shape = 0;
+    // Launch shape (msim_kernel.cu) = register budget against resident warps.  Measured on a B200
+    // (profiles/r02_launch_shape_sweep_*.jsonl): 56 registers x 36 warps per SM is the best trade for every workload
+    // that shared memory lets reach it; a handle that shared memory holds at <= 32 warps takes the 64-register build.
+    // Diagnostics for sweeps (tools/occupancy_sweep.sh): MSIM_SHAPE = 0 / 1 / 2 forces a shape, MSIM_MAX_CTAS_PER_SM
+    // caps the resident CTAs per SM, MSIM_WARPS_PER_CTA fixes the CTA width.
+    int cta_cap = 0, w_fixed = 0, shape_forced = -1;
     if (const char* e = getenv("MSIM_MAX_CTAS_PER_SM")) cta_cap = atoi(e);
     if (const char* e = getenv("MSIM_WARPS_PER_CTA")) w_fixed = atoi(e);
-    if (const char* e = getenv("MSIM_SHAPE")) shape = atoi(e);
-    if (shape < 0 || shape > 2) { delete h; return fail(MSIM_E_INVALID, "MSIM_SHAPE must be 0, 1 or 2"); }
-    h->shape = shape;
-    for (int rng = 0; rng < 2; ++rng) {
-        int best_w = 0, best_total = 0, best_blocks = 0;
+    if (const char* e = getenv("MSIM_SHAPE")) shape_forced = atoi(e);
+    if (shape_forced > 2) { delete h; return fail(MSIM_E_INVALID, "MSIM_SHAPE must be 0, 1 or 2"); }
+    struct Fit { int w, blocks, total, regs; };
+    int rc_fit = 0;
+    auto fit = [&](int shape, int rng) {
+        Fit f{0, 0, 0, 0};
         for (int w = 1; w <= sim_shape_max_warps(shape); ++w) {
             if (w_fixed > 0 && w != w_fixed) continue;
             size_t need = (size_t)w * L.slab_bytes;
             if (need > smem_blk_max) break;
             int nblk = 0, regs = 0;
             int rc = sim_kernel_attrs(h->policy, rng, shape, need, &regs, w * 32, &nblk);
-            if (rc != 0) {
-                delete h;
-                return fail(rc, rc == MSIM_E_UNSUPPORTED ? "policy not available in this build" : "kernel attribute query failed");
-            }
-            h->regs[rng] = regs;
+            if (rc != 0) { rc_fit = rc; return f; }
+            f.regs = regs;
             if (cta_cap > 0 && nblk > cta_cap) nblk = cta_cap;
-            int warps = nblk * w;
-            if (warps > best_total || (warps == best_total && w > best_w)) { best_total = warps; best_w = w; best_blocks = nblk; }
+            if (nblk * w > f.total || (nblk * w == f.total && w > f.w)) { f.total = nblk * w; f.w = w; f.blocks = nblk; }
         }
-        if (best_total == 0) { delete h; return fail(MSIM_E_UNSUPPORTED, "scenario does not fit shared memory"); }
-        h->warps_per_block[rng] = best_w;
-        h->blocks_per_sm[rng] = best_blocks;
-        h->smem_bytes[rng] = (size_t)best_w * L.slab_bytes;
+        return f;
+    };
+    int shape = shape_forced >= 0 ? shape_forced : 1;
+    if (shape_forced < 0) {
+        Fit f1 = fit(1, MSIM_RNG_PHILOX), f0 = fit(0, MSIM_RNG_PHILOX);
+        if (rc_fit == 0 && f0.total >= f1.total) shape = 0;      // no residency to gain from the smaller register budget
+    }
+    h->shape = shape;
+    for (int rng = 0; rng < 2 && rc_fit == 0; ++rng) {
+        Fit f = fit(shape, rng);
+        if (rc_fit != 0) break;
+        if (f.total == 0) { delete h; return fail(MSIM_E_UNSUPPORTED, "scenario does not fit shared memory"); }
+        h->regs[rng] = f.regs;
+        h->warps_per_block[rng] = f.w;
+        h->blocks_per_sm[rng] = f.blocks;
+        h->smem_bytes[rng] = (size_t)f.w * L.slab_bytes;
+    }
+    if (rc_fit != 0) {
+        delete h;
+        return fail(rc_fit, rc_fit == MSIM_E_UNSUPPORTED ? "policy not available in this build" : "kernel attribute query failed");
     }
     if (cudaMalloc(&h->d_counter, 8) != cudaSuccess) {
         delete h;

@@ -25,6 +25,10 @@ sys.path.insert(0, str(ROOT))
 
 # round-2 history (profiles/r02_ab_probe.jsonl): tailpush +10 %, lean +15..23 %, lb4 +12 % where shared memory limits the
 # handle to 4 CTAs per SM -> folded into the default build; flushgrp -5 %, duecache -5 %, ropecache 0, nto 0 -> removed.
+# second batch (profiles/r02_ab_diet_*.jsonl, patch kept as tools/experiments/r02_code_diet.patch): delivery mode as a
+# template parameter + one flush site + cold draws out of line -5 %, calendar pop through the attention word +3 % on top of
+# that, per-stripe earliest onDue timer +2 % -- none beat the plain build, whose 36 KB hot set sits right at the
+# instruction-cache capacity: the response to small code changes is dominated by layout, not by instruction count.
 VARIANTS = {
 }
 RESTRICTED = set()

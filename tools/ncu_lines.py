@@ -40,9 +40,9 @@ for s, (kk, f, hi) in enumerate(kern):
         ln = int(r[0]); v = int(r[ie] or 0); smp = int(r[isamp] or 0)
         key = region(ln) if "msim_kernel" in f else f
         ex[key] += v; st[key] += smp
-        if r[2].startswith("0x"): sz[key] += 16
+        if len(r) > 2 and r[2].strip().startswith("0x"): sz[key] += 16
         if "msim_kernel" in f:
-            e = per_line.setdefault(ln, [0, 0, 0, r[1]]); e[0] += v; e[1] += 16 if r[2].startswith("0x") else 0; e[2] += smp
+            e = per_line.setdefault(ln, [0, 0, 0, r[1]]); e[0] += v; e[1] += 16 if (len(r) > 2 and r[2].strip().startswith("0x")) else 0; e[2] += smp
 T, S, Z = sum(ex.values()), sum(st.values()), sum(sz.values())
 print(f"kernel {a.kernel}: {T / a.events:.1f} warp instr/event, {Z / 1024:.1f} KB SASS, {S} stall samples")
 print(" instr/ev   KB   stall%  region")

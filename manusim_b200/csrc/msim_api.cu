@@ -246,7 +246,7 @@ extern "C" int msim_create(const msim_tables_t* t, msim_handle_t* out) {
             size_t need = (size_t)w * L.slab_bytes;
             if (need > smem_blk_max) break;
             int nblk = 0, regs = 0;
-            int rc = sim_kernel_attrs(h->policy, rng, shape, need, &regs, w * 32, &nblk);
+            int rc = sim_kernel_attrs(h->policy, rng, shape, on_due, need, &regs, w * 32, &nblk);
             if (rc != 0) { rc_fit = rc; return f; }
             f.regs = regs;
             if (cta_cap > 0 && nblk > cta_cap) nblk = cta_cap;
@@ -255,10 +255,11 @@ extern "C" int msim_create(const msim_tables_t* t, msim_handle_t* out) {
         return f;
     };
     int shape = shape_forced >= 0 ? shape_forced : 1;
-    if (shape_forced < 0) {
+    if (shape_forced < 0 && sim_shape_compiled(0) == 0) {
         Fit f1 = fit(1, MSIM_RNG_PHILOX), f0 = fit(0, MSIM_RNG_PHILOX);
         if (rc_fit == 0 && f0.total >= f1.total) shape = 0;      // no residency to gain from the smaller register budget
     }
+    shape = sim_shape_compiled(shape);
     h->shape = shape;
     for (int rng = 0; rng < 2 && rc_fit == 0; ++rng) {
         Fit f = fit(shape, rng);

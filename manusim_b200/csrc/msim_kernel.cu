@@ -44,6 +44,9 @@
 // cached earliest onDue / rope timer (-5 % / 0: the extra code costs more than the scan it saves), counting calendar
 // pops at the end (0).  (Byte-identical SASS, hence never timed: __builtin_expect on the error / option branches, an
 // equality chain on the hottest micro-events in front of the handler switch.)
+#ifndef MSIM_ALL_SHAPES    // 1: also compile the 64- and 48-register shapes of the lean kernels (sweeps); default: 56 only
+#define MSIM_ALL_SHAPES 0
+#endif
 #ifndef MSIM_X_F32CELL     // 1 = NEGATIVE CONTROL for tests/test_emu_kernel.py: order the DBR calendar by float32 time alone
 #define MSIM_X_F32CELL 0   //     (the round-1 behaviour; golden dbr_f64_order must fail with it)
 #endif
@@ -53,9 +56,9 @@
 // SHAPE = the launch bounds, i.e. the register budget against the resident warps (profiles/r02_launch_shape_sweep_c.jsonl:
 // at EQUAL residency the 64-register build is 31 % faster than the 48-register one, whose spills sit on lane 0's
 // critical path; 64 registers at 32 warps per SM beat 48 registers at 40 by 15 %):
-//   0: __launch_bounds__(256, 4) -> 64 registers, <= 32 warps per SM   (default, every kernel)
-//   1: __launch_bounds__(192, 6) -> 56 registers, <= 36 warps per SM   (lean kernels only)
-//   2: __launch_bounds__(256, 5) -> 48 registers, <= 40 warps per SM   (lean kernels only; the round-1 shape)
+//   0: __launch_bounds__(256, 4) -> 64 registers, <= 32 warps per SM   (-DMSIM_ALL_SHAPES=1 only)
+//   1: __launch_bounds__(192, 6) -> 56 registers, <= 36 warps per SM   (the build: best on every measured workload)
+//   2: __launch_bounds__(256, 5) -> 48 registers, <= 40 warps per SM   (-DMSIM_ALL_SHAPES=1 only; the round-1 shape)
 #define LOGQ (((OPTS) & 1) && p.log_queues)
 #define RECORDING (((OPTS) & 2) && p.a.rec_cap > 0)
 #define NOT_RECORDING (!((OPTS) & 2) || p.a.rec_cap == 0)
@@ -192,7 +195,17 @@ __device__ __noinline__ double philox_draw_slow(const KParams& p, Scal* sc, cons
     return out;
 }
 
-template <int POLICY, int RNG, int OPTS>
+// MODE: 0 = the handle delivers asReady or instantly (told apart at run time, a few instructions in INIT_SHIP), 1 = onDue
+// (per-order delivery timers in the calendar), 2 = decided at run time from KParams (the general OPTS = 3 kernels).  The
+// kernel is instruction-fetch bound: compiling the other mode's code out is worth more than the branch it removes.
+// replay mode: next value of tape `stream` (A, B, D); an exhausted tape ends the replication with a status code
+__device__ __noinline__ float replay_scalar(Scal* sc, int stream) {
+    const uint32_t idx = sc->draw[stream]++;
+    if (idx >= sc->tlen[stream]) { sc->x_status = MSIM_ST_TAPE_EXHAUSTED; return 0.0f; }
+    return __ldg(reinterpret_cast<const float*>(sc->tbase[stream]) + idx);
+}
+
+template <int POLICY, int RNG, int OPTS, int MODE>
 struct Sim {
     const KParams& p;
     unsigned char* sb;        // this warp's slab
@@ -213,6 +226,7 @@ struct Sim {
     double& now_d;            // DBR only: exact python-typed clock (now is its float32 view)
     static constexpr bool DBR = POLICY == MSIM_POLICY_DBR;
     static constexpr bool PRIO = POLICY == MSIM_POLICY_MAX_PRIORITY || POLICY == MSIM_POLICY_EDD;
+    __device__ __forceinline__ bool on_due() const { return MODE == 2 ? p.delivery_mode == MSIM_DELIVERY_ON_DUE : MODE == 1; }
 
     __device__ __forceinline__ Sim(const KParams& p_, unsigned char* sb_, Scal* sc_)
         : p(p_), sb(sb_), sc(sc_), uqh(sc_->x_uqh), uqt(sc_->x_uqt), logc(sc_->x_logc), tseq(sc_->x_tseq),
@@ -281,6 +295,8 @@ struct Sim {
         if (fast_sample(stream, d, v)) return v > 0.0f ? v : 0.0f;
         return (float)philox_draw_slow<OPTS>(p, sc, ARR(float2, rb), rep, stream, &d, -1);
     }
+    // scalar draws of the COLD call sites (demand triplets, breakdowns, boot): one call, no inlined fast path -- the kernel
+    // is instruction-fetch bound and these sites run once per order or less (constants are handled inside the callee)
     __device__ __forceinline__ float draw_scalar(int stream, const DDist& d) {
         if (RNG == MSIM_RNG_REPLAY) {
             uint32_t idx = sc->draw[stream]++;
@@ -843,7 +859,7 @@ struct Sim {
         case OP_INIT_SHIP:                                       // :482-549 (onDue with patch P1)
             // (one finished_goods.get() site for the three delivery modes and the onDue timer: the handler switch is
             //  instruction-cache bound, inlined copies cost more than the branches)
-            if (p.delivery_mode == MSIM_DELIVERY_INSTANTLY) {
+            if (!on_due() && p.delivery_mode == MSIM_DELIVERY_INSTANTLY) {
                 if (!(PRD(float, fg, a) >= DORD(float, qty, b))) {      // lost sale: nothing is taken
                     if (warm) {
                         inventory(a, false, true);
@@ -853,7 +869,7 @@ struct Sim {
                     free_do(b);
                     break;
                 }
-            } else if (p.delivery_mode == MSIM_DELIVERY_ON_DUE) {
+            } else if (on_due()) {
                 float wait = __fsub_rn(DORD(float, due, b), now);
                 if (wait > 0.0f) {
                     float t = __fadd_rn(now, wait);
@@ -1009,7 +1025,8 @@ struct Sim {
     // (SURVEY Appendix A.8): URGENT fifo -> calendar entries landing on `now` -> NORMAL fifo.
     // `first` = the calendar event the warp just selected (0 = none): it runs before anything queued, because the
     // URGENT fifo is empty whenever the calendar is consulted.
-    __device__ __forceinline__ int drain(uint32_t first) {
+    // (two shapes of the same loop, chosen per kernel family at compile time: LOOP2 in sim_kernel)
+    __device__ __forceinline__ int drain1(uint32_t first) {
         for (;;) {
             uint32_t ev;
             if (first) {                 // (single dispatch site: the handler switch must not be inlined twice)
@@ -1036,6 +1053,38 @@ struct Sim {
             }
             dispatch(ev);
             if (nqt - nqh > (uint32_t)p.lay.NQ) fail(MSIM_ST_FIFO_OVERFLOW);
+        }
+    }
+
+    __device__ __forceinline__ int drain2() {
+        for (;;) {
+            uint32_t ev;
+            if (attn) {
+                if (attn & A_STATUS) return REQ_DONE;
+                if (attn & A_SELECT) { attn &= ~A_SELECT; return REQ_SELECT; }
+                if (attn & A_FLUSH) { attn &= ~A_FLUSH; return REQ_FLUSH; }
+                if (attn & A_PENDING) {      // the calendar entry the warp just selected (or Initialize[scheduler] at boot)
+                    ev = pending;
+                    attn &= ~A_PENDING;
+                } else if (attn & A_URGENT) {
+                    ev = ARR(uint32_t, uq)[uqh & (uint32_t)(p.lay.UQ - 1)];
+                    uqh++;
+                    if (uqh == uqt) attn &= ~A_URGENT;
+                } else {
+                    return REQ_ADVANCE;      // A_SAME: calendar entries at `now` precede NORMAL events created at `now`
+                }
+            } else {
+                // one unsigned compare covers both ends: empty fifo (d - 1 wraps) and overrun (d > NQ)
+                const uint32_t d = nqt - nqh;
+                if (d - 1u >= (uint32_t)p.lay.NQ) {
+                    if (d == 0u) return REQ_ADVANCE;
+                    fail(MSIM_ST_FIFO_OVERFLOW);
+                    return REQ_DONE;
+                }
+                ev = ARR(uint32_t, nq)[nqh & (uint32_t)(p.lay.NQ - 1)];
+                nqh++;
+            }
+            dispatch(ev);       // (single dispatch site: the handler switch must not be inlined twice)
         }
     }
 
@@ -1152,7 +1201,7 @@ __device__ __forceinline__ void warp_flush(const KParams& p, const unsigned char
 constexpr int shape_threads(int shape) { return shape == 1 ? 192 : 256; }
 constexpr int shape_ctas(int shape) { return shape == 1 ? 6 : (shape == 2 ? 5 : 4); }
 
-template <int POLICY, int RNG, int OPTS, int SHAPE>
+template <int POLICY, int RNG, int OPTS, int SHAPE, int MODE>
 __global__ void __launch_bounds__(shape_threads(SHAPE), shape_ctas(SHAPE)) sim_kernel(const __grid_constant__ KParams p) {
     MSIM_DYN_SMEM(smem);
     const Lay& L = p.lay;
@@ -1160,9 +1209,10 @@ __global__ void __launch_bounds__(shape_threads(SHAPE), shape_ctas(SHAPE)) sim_k
     const int warp = threadIdx.x >> 5;
     unsigned char* sb = smem + (size_t)warp * L.slab_bytes;
     Scal* sc = reinterpret_cast<Scal*>(sb + L.scal);
-    Sim<POLICY, RNG, OPTS> s(p, sb, sc);
-    const bool on_due = p.delivery_mode == MSIM_DELIVERY_ON_DUE;
+    Sim<POLICY, RNG, OPTS, MODE> s(p, sb, sc);
+    const bool on_due = s.on_due();
     constexpr bool DBR = POLICY == MSIM_POLICY_DBR;
+    constexpr bool LOOP2 = POLICY != MSIM_POLICY_FIFO;      // loop shape per kernel family (see the event loop below)
     constexpr int kPoStride = aos_po_stride(POLICY), kDoStride = kAosDoLinkStride;
     const uint32_t until_bits = __float_as_uint(p.run_until);
 
@@ -1218,23 +1268,49 @@ __global__ void __launch_bounds__(shape_threads(SHAPE), shape_ctas(SHAPE)) sim_k
             }
         }
         __syncwarp();
-        uint32_t first_ev = 0;
         if (lane == 0) s.boot();
         __syncwarp();
 
-        // ---- event loop
+        // ---- event loop.  Two shapes of the loop head, same semantics; which one a kernel family gets was decided on the
+        // B200 (profiles/r02_ab_variants_*.jsonl -- the kernel is instruction-fetch bound and responds to code layout more
+        // than to instruction count): LOOP2 hands the selected calendar entry to lane 0 through the attention word and has
+        // ONE flush site (`finishing`, warp-uniform: the replication is over, one more pass writes out what is staged);
+        // the other shape passes it as an argument and flushes again after the loop.
+        uint32_t first_ev = 0;
+        bool finishing = false;
         for (;;) {
-            int req = REQ_ADVANCE;
-            if (lane == 0) { req = s.drain(first_ev); first_ev = 0; }
-            req = __shfl_sync(FULLMASK, req, 0);
-            uint32_t n = __shfl_sync(FULLMASK, s.nstage, 0);
-            if (req == REQ_FLUSH) {
-                warp_flush(p, sb, rep, lane, n, __shfl_sync(FULLMASK, s.logc, 0));
-                if (lane == 0) { s.logc += n; s.nstage = 0; }
-                __syncwarp();
-                continue;
+            int req;
+            if constexpr (LOOP2) {
+                req = REQ_FLUSH;
+                if (!finishing) {
+                    req = REQ_ADVANCE;
+                    if (lane == 0) req = s.drain2();
+                    req = __shfl_sync(FULLMASK, req, 0);
+                    if (req == REQ_DONE) { finishing = true; continue; }
+                }
+                if (req == REQ_FLUSH) {
+                    const uint32_t n = __shfl_sync(FULLMASK, s.nstage, 0);
+                    if (n > 0) {
+                        warp_flush(p, sb, rep, lane, n, __shfl_sync(FULLMASK, s.logc, 0));
+                        if (lane == 0) { s.logc += n; s.nstage = 0; }
+                        __syncwarp();
+                    }
+                    if (finishing) break;
+                    continue;
+                }
+            } else {
+                req = REQ_ADVANCE;
+                if (lane == 0) { req = s.drain1(first_ev); first_ev = 0; }
+                req = __shfl_sync(FULLMASK, req, 0);
+                uint32_t n = __shfl_sync(FULLMASK, s.nstage, 0);
+                if (req == REQ_FLUSH) {
+                    warp_flush(p, sb, rep, lane, n, __shfl_sync(FULLMASK, s.logc, 0));
+                    if (lane == 0) { s.logc += n; s.nstage = 0; }
+                    __syncwarp();
+                    continue;
+                }
+                if (req == REQ_DONE) break;
             }
-            if (req == REQ_DONE) break;
             if (DBR && req == REQ_SELECT) {
                 // ---- cooperative DBR dispatch (toc_dbr/simulation.py:291-328): for every queued order, the
                 // quantity of same-product orders released strictly earlier that sit in ANY input/output/transport/
@@ -1329,7 +1405,9 @@ __global__ void __launch_bounds__(shape_threads(SHAPE), shape_ctas(SHAPE)) sim_k
                 }
             }
             const uint32_t tbits = __reduce_min_sync(FULLMASK, bt);
-            if (tbits >= until_bits) break;      // the URGENT stop event at run_until precedes everything at that time
+            if (tbits >= until_bits) {           // the URGENT stop event at run_until precedes everything at that time
+                if constexpr (LOOP2) { finishing = true; continue; } else break;
+            }
             const bool mine = bt == tbits;
             const uint32_t emin = __reduce_min_sync(FULLMASK, mine ? be : 0xFFFFFFFFu);
             const uint32_t cnt = __reduce_add_sync(FULLMASK, mine ? (uint32_t)leq : 0u);
@@ -1343,7 +1421,8 @@ __global__ void __launch_bounds__(shape_threads(SHAPE), shape_ctas(SHAPE)) sim_k
                     (reinterpret_cast<const uint32_t*>(sb + L.nq)[s.nqh & (uint32_t)(L.NQ - 1)] & EV_PY) != 0u;
                 slot = dbr_cell_order(p, sb, sc, tbits, slot0, s.now_d, head_py);
                 if (slot < 0) {                              // the fifo head belongs to an earlier float64 instant
-                    first_ev = reinterpret_cast<const uint32_t*>(sb + L.nq)[s.nqh & (uint32_t)(L.NQ - 1)];
+                    const uint32_t head_ev = reinterpret_cast<const uint32_t*>(sb + L.nq)[s.nqh & (uint32_t)(L.NQ - 1)];
+                    if constexpr (LOOP2) { s.pending = head_ev; s.attn |= A_PENDING; } else first_ev = head_ev;
                     s.nqh++;
                 }
             }
@@ -1374,7 +1453,7 @@ __global__ void __launch_bounds__(shape_threads(SHAPE), shape_ctas(SHAPE)) sim_k
                             s.now_py = 1; s.now_d = sc->tick_d;
                         }
                     }
-                } else if (slot < L.NT + L.MD) {
+                } else if (on_due && slot < L.NT + L.MD) {
                     int d = slot - L.NT;
                     ev = EV(OP_TO_SHIP, DORD(uint8_t, prod, d), d);
                     reinterpret_cast<float*>(sb + L.do_tt)[d] = CUDART_INF_F;
@@ -1383,13 +1462,14 @@ __global__ void __launch_bounds__(shape_threads(SHAPE), shape_ctas(SHAPE)) sim_k
                     ev = EV(OP_TO_DORDER, 0, po);
                     reinterpret_cast<float*>(sb + L.po_tt)[po] = CUDART_INF_F;
                 }
-                first_ev = DBR ? ev | (s.now_py << 24) : ev;
+                // (it runs before anything queued: the URGENT fifo is empty whenever the calendar is consulted)
+                if constexpr (LOOP2) { s.pending = DBR ? ev | (s.now_py << 24) : ev; s.attn |= A_PENDING; }
+                else first_ev = DBR ? ev | (s.now_py << 24) : ev;
             }
             __syncwarp();
         }
 
-        // ---- final flush + per-replication outputs
-        {
+        if constexpr (!LOOP2) {
             uint32_t n = __shfl_sync(FULLMASK, s.nstage, 0);
             if (n > 0) {
                 warp_flush(p, sb, rep, lane, n, __shfl_sync(FULLMASK, s.logc, 0));
@@ -1397,6 +1477,7 @@ __global__ void __launch_bounds__(shape_threads(SHAPE), shape_ctas(SHAPE)) sim_k
                 __syncwarp();
             }
         }
+        // ---- per-replication outputs
         if (lane == 0) {
             p.a.n_events[rep] = (unsigned long long)s.nev + 1ull;     // + the stop event of run(until)
             p.a.status[rep] = s.status;
@@ -1412,33 +1493,45 @@ __global__ void __launch_bounds__(shape_threads(SHAPE), shape_ctas(SHAPE)) sim_k
 
 // ---------------------------------------------------------------------------------------------------------
 typedef void (*sim_fn)(const KParams);
-template <int OPTS, int SHAPE>
+template <int OPTS, int SHAPE, int MODE>
 static sim_fn pick_rng(int policy, int rng) {
-    if (policy == MSIM_POLICY_FIFO) return rng == MSIM_RNG_REPLAY ? sim_kernel<MSIM_POLICY_FIFO, MSIM_RNG_REPLAY, OPTS, SHAPE>
-                                                                  : sim_kernel<MSIM_POLICY_FIFO, MSIM_RNG_PHILOX, OPTS, SHAPE>;
+    if (policy == MSIM_POLICY_FIFO)
+        return rng == MSIM_RNG_REPLAY ? sim_kernel<MSIM_POLICY_FIFO, MSIM_RNG_REPLAY, OPTS, SHAPE, MODE>
+                                      : sim_kernel<MSIM_POLICY_FIFO, MSIM_RNG_PHILOX, OPTS, SHAPE, MODE>;
     if (policy == MSIM_POLICY_MAX_PRIORITY)
-        return rng == MSIM_RNG_REPLAY ? sim_kernel<MSIM_POLICY_MAX_PRIORITY, MSIM_RNG_REPLAY, OPTS, SHAPE>
-                                      : sim_kernel<MSIM_POLICY_MAX_PRIORITY, MSIM_RNG_PHILOX, OPTS, SHAPE>;
+        return rng == MSIM_RNG_REPLAY ? sim_kernel<MSIM_POLICY_MAX_PRIORITY, MSIM_RNG_REPLAY, OPTS, SHAPE, MODE>
+                                      : sim_kernel<MSIM_POLICY_MAX_PRIORITY, MSIM_RNG_PHILOX, OPTS, SHAPE, MODE>;
     if (policy == MSIM_POLICY_DBR)
-        return rng == MSIM_RNG_REPLAY ? sim_kernel<MSIM_POLICY_DBR, MSIM_RNG_REPLAY, OPTS, SHAPE>
-                                      : sim_kernel<MSIM_POLICY_DBR, MSIM_RNG_PHILOX, OPTS, SHAPE>;
+        return rng == MSIM_RNG_REPLAY ? sim_kernel<MSIM_POLICY_DBR, MSIM_RNG_REPLAY, OPTS, SHAPE, MODE>
+                                      : sim_kernel<MSIM_POLICY_DBR, MSIM_RNG_PHILOX, OPTS, SHAPE, MODE>;
     if (policy == MSIM_POLICY_EDD)
-        return rng == MSIM_RNG_REPLAY ? sim_kernel<MSIM_POLICY_EDD, MSIM_RNG_REPLAY, OPTS, SHAPE>
-                                      : sim_kernel<MSIM_POLICY_EDD, MSIM_RNG_PHILOX, OPTS, SHAPE>;
+        return rng == MSIM_RNG_REPLAY ? sim_kernel<MSIM_POLICY_EDD, MSIM_RNG_REPLAY, OPTS, SHAPE, MODE>
+                                      : sim_kernel<MSIM_POLICY_EDD, MSIM_RNG_PHILOX, OPTS, SHAPE, MODE>;
     return nullptr;
 }
-// lean: the run uses neither queue records nor tape recording (OPTS = 0); the general kernels exist in shape 0 only
-static sim_fn pick(int policy, int rng, bool lean, int shape) {
-    if (!lean) return pick_rng<3, 0>(policy, rng);
-    return shape == 1 ? pick_rng<0, 1>(policy, rng) : (shape == 2 ? pick_rng<0, 2>(policy, rng) : pick_rng<0, 0>(policy, rng));
+template <int SHAPE>
+static sim_fn pick_lean(int policy, int rng, bool on_due) {
+    return on_due ? pick_rng<0, SHAPE, 1>(policy, rng) : pick_rng<0, SHAPE, 0>(policy, rng);
+}
+// lean: the run uses neither queue records nor tape recording (OPTS = 0) -> one kernel per delivery family; the general
+// kernels (OPTS = 3) decide the delivery mode at run time and exist in the default shape only.  Shapes 0 and 2 are
+// compiled with -DMSIM_ALL_SHAPES=1 (launch-shape sweeps); otherwise every request falls back to shape 1.
+static sim_fn pick(int policy, int rng, bool lean, int shape, bool on_due) {
+    if (!lean) return pick_rng<3, 1, 2>(policy, rng);
+#if MSIM_ALL_SHAPES
+    if (shape == 0) return pick_lean<0>(policy, rng, on_due);
+    if (shape == 2) return pick_lean<2>(policy, rng, on_due);
+#endif
+    return pick_lean<1>(policy, rng, on_due);
 }
 
+int sim_shape_compiled(int shape) { return MSIM_ALL_SHAPES ? shape : 1; }
 int sim_shape_max_warps(int shape) { return shape_threads(shape) / 32; }
 
-int sim_kernel_attrs(int policy, int rng_mode, int shape, size_t smem, int* regs, int block, int* blocks_per_sm) {
-    // residency of the LEAN kernel of this shape, bounded by the general kernel's (shape 0) with the same CTA: a run that
-    // records tapes or logs queue lengths launches that one with the same grid
-    sim_fn f = pick(policy, rng_mode, true, shape), g = pick(policy, rng_mode, false, 0);
+int sim_kernel_attrs(int policy, int rng_mode, int shape, bool on_due, size_t smem, int* regs, int block, int* blocks_per_sm) {
+    // residency of the LEAN kernel of this shape; a run that records tapes or logs queue lengths launches the general
+    // kernel with the same grid (CTAs that do not fit simply queue)
+    sim_fn f = pick(policy, rng_mode, true, shape, on_due), g = pick(policy, rng_mode, false, shape, on_due);
     if (!f || !g) return MSIM_E_UNSUPPORTED;
     cudaFuncAttributes at;
     if (cudaFuncGetAttributes(&at, f) != cudaSuccess) return MSIM_E_CUDA;
@@ -1459,7 +1552,7 @@ int launch_sim(const KParams& p, int policy, int rng_mode, int shape, int grid, 
     // MSIM_NO_LEAN=1 (diagnostic, tests): always launch the general kernel
     const char* no_lean = getenv("MSIM_NO_LEAN");
     const bool lean = !p.log_queues && p.a.rec_cap == 0 && !(no_lean && no_lean[0] == '1');
-    sim_fn f = pick(policy, rng_mode, lean, shape);
+    sim_fn f = pick(policy, rng_mode, lean, shape, p.delivery_mode == MSIM_DELIVERY_ON_DUE);
     if (!f) return MSIM_E_UNSUPPORTED;
     // The opt-in shared-memory limit is per FUNCTION, not per handle: handles with different slab sizes share a kernel
     // and msim_create lowers the attribute again while it probes CTA widths, so it is set before every launch (a host-

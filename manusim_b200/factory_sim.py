@@ -77,6 +77,28 @@ class FactorySimulation:
                                                        dbr_repair=self.dbr_repair, **engine_opts)
         self._initiate_environment()
 
+    def monitor_steps(self) -> int:
+        """`Environment.step()` calls the reference's console monitor adds to a run (factory_sim.py:656-684): with
+        print_mode in {"all", "metrics", "status"} -- "metrics" is the constructor default -- `_run_monitor` starts one more
+        process: its Initialize event, the Timeout(monitor_warmup) and one Timeout(monitor_interval) per report, each
+        counted while its instant lies before run_until (the URGENT stop event precedes anything scheduled at run_until).
+        The monitor only prints; it logs nothing and changes no other event's order, so records and metrics are the same
+        with and without it -- the engine does not print progress reports, it only counts these steps in `sim_events`."""
+        if self.print_mode not in ("all", "metrics", "status"):
+            return 0
+        steps = 1                                              # Initialize[_monitor]
+        t, dt = self.monitor_warmup, self.monitor_interval
+        if not (t < self.run_until):
+            return steps
+        if not (dt > 0):
+            raise ValueError("monitor_interval must be positive (the reference's monitor would never advance)")
+        k = int((self.run_until - t) / dt)                     # number of k >= 0 with t + k * dt < run_until, exactly
+        while t + k * dt >= self.run_until:
+            k -= 1
+        while t + (k + 1) * dt < self.run_until:
+            k += 1
+        return 1 + (k + 1)
+
     # ------------------------------------------------------------------ hook policing
     def _check_hooks(self):
         for name in _HOOKS:
@@ -191,7 +213,7 @@ class FactorySimulation:
             raise RuntimeError(f"replication failed: {STATUS_TEXT.get(status, status)}")
         self.env.now = self.run_until
         self.warmup_finished = True
-        self.sim_events = int(res.n_events[0])
+        self.sim_events = int(res.n_events[0]) + self.monitor_steps()
         self._acc = (res.acc_sum[0].cpu().numpy(), res.acc_cnt[0].cpu().numpy())
         if n_log:
             count = int(res.log_count[0])

@@ -70,14 +70,25 @@ def flat_slices(n_scenarios: int, reps: int, world: int, rank: int) -> List[Tupl
 
 class SweepRunner:
     def __init__(self, sim_cls, base: Dict[str, Any], overrides: Dict[str, Sequence[Any]], reps: int, seed: int = 0,
-                 sim_kwargs: Dict[str, Any] | None = None):
+                 sim_kwargs: Dict[str, Any] | None = None, streams: int = 8):
+        """`streams`: scenario slices are launched round-robin on this many CUDA streams and nobody waits for a single
+        scenario: the persistent grids of consecutive scenarios overlap, so a scenario's tail wave (and a fine grid's tiny
+        launches) run next to the following scenarios' bodies.  The host synchronises once, after the last launch; pool
+        overflows are re-run then (the reduction skips failed replications, a re-run adds its own contribution)."""
         self.sim_cls = sim_cls
         self.points = expand_grid(base, overrides)
         self.reps = reps
         self.seed = seed
         self.sim_kwargs = sim_kwargs or {}
+        self.streams = max(1, int(streams))
         self.moments = None
         self.events = 0
+        self.launches = 0
+        self.reruns = 0
+
+    def _new_sim(self, s):
+        _, tree = self.points[s]
+        return self.sim_cls(tree["simulation"], tree["resources"], tree["products"], print_mode="none", **self.sim_kwargs)
 
     def run(self) -> pd.DataFrame:
         import torch
@@ -85,37 +96,48 @@ class SweepRunner:
 
         world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
         rank = dist.get_rank() if world > 1 else 0
-        sims = {}
-        mom = None
-        ev_total = None
-        names = None
-        for s, first, cnt in flat_slices(len(self.points), self.reps, world, rank):
-            if s not in sims:
-                _, tree = self.points[s]
-                sims[s] = self.sim_cls(tree["simulation"], tree["resources"], tree["products"], print_mode="none",
-                                       **self.sim_kwargs)
-            sim = sims[s]
-            eng = sim.engine
-            if mom is None:
-                mom = torch.zeros((len(self.points), eng.K, 3), dtype=torch.float64, device=eng.device)
-                ev_total = torch.zeros((), dtype=torch.int64, device=eng.device)
-                names = sim.tables.ring_names()
+        slices = flat_slices(len(self.points), self.reps, world, rank)
+        first_sim = self._new_sim(slices[0][0] if slices else 0)
+        eng0 = first_sim.engine
+        dev = eng0.device
+        names = first_sim.tables.ring_names()
+        mom = torch.zeros((len(self.points), eng0.K, 3), dtype=torch.float64, device=dev)
+        ev_total = torch.zeros((), dtype=torch.int64, device=dev)
+        main = torch.cuda.current_stream(dev)
+        pool = [torch.cuda.Stream(dev) for _ in range(min(self.streams, max(1, len(slices))))]
+        start = torch.cuda.Event()
+        start.record(main)
+        for st in pool:
+            st.wait_event(start)
+        pending = []                                   # (sim, result, scenario, first, count): kept alive until the sync
+        sims = {slices[0][0]: first_sim} if slices else {}
+        for i, (s, first, cnt) in enumerate(slices):
+            sim = sims.get(s) or sims.setdefault(s, self._new_sim(s))
+            st = pool[i % len(pool)]
             # replication key = f(seed of the scenario, replication index within the scenario): shard-invariant
-            res = eng.run(cnt, seed=self.seed + 1000003 * s, rep_offset=first)
-            eng.retry_overflow(res, seed=self.seed + 1000003 * s, rep_offset=first)
-            eng.reduce(res, out=mom[s])
+            with torch.cuda.stream(st):
+                res = sim.engine.run(cnt, seed=self.seed + 1000003 * s, rep_offset=first, stream=st)
+                sim.engine.reduce(res, out=mom[s], stream=st)
+            self.launches += 1
+            pending.append((sim, res, s, first, cnt))
+        for st in pool:
+            done = torch.cuda.Event()
+            done.record(st)
+            main.wait_event(done)
+        torch.cuda.synchronize(dev)
+        # re-run what overflowed the shared-memory pools (few replications, largest pools): the first reduction skipped
+        # them, so the re-run's own result adds exactly their contribution
+        for sim, res, s, first, cnt in pending:
+            ctx = sim.engine.retry_launch(res, seed=self.seed + 1000003 * s, rep_offset=first)
+            if ctx is not None:
+                self.reruns += sim.engine.retry_collect(ctx)
+                sim.engine.reduce(ctx[3], out=mom[s])
+        for sim, res, s, first, cnt in pending:
             ev_total += res.n_events.sum()
-        if mom is None:   # a rank without work still has to join the collective
-            sim = self.sim_cls(*[self.points[0][1][k] for k in ("simulation", "resources", "products")],
-                               print_mode="none", **self.sim_kwargs)
-            eng = sim.engine
-            mom = torch.zeros((len(self.points), eng.K, 3), dtype=torch.float64, device=eng.device)
-            ev_total = torch.zeros((), dtype=torch.int64, device=eng.device)
-            names = sim.tables.ring_names()
         if world > 1:
             dist.all_reduce(mom)
             dist.all_reduce(ev_total)
-        torch.cuda.synchronize()
+        torch.cuda.synchronize(dev)
         self.moments = mom.cpu().numpy()
         self.events = int(ev_total.item())
         frames = []

@@ -32,13 +32,13 @@ def scenarios_table():
 
     out = {}
     sim, res, prod, _ = rr.load_example("simple_scheduler")
-    sim = dict(copy.deepcopy(sim), memory_size=200000)
+    sim = dict(copy.deepcopy(sim), memory_size=20000)
     sim.pop("print_mode", None)
     # config #1 as shipped (run_until 1000, warm-up 50, max-priority dispatch)
     out["stats_ss_cfg1"] = dict(cfg=sim, resources=res, products=prod, policy="simple_scheduler", patches=[], exp_seed=123)
     # config #3 shortened: examples/toc_dbr repaired, run_until 20 001 / warm-up 2 000
     simd, resd, prodd, _ = rr.load_example("toc_dbr")
-    simd = dict(copy.deepcopy(simd), run_until=20001, warmup=2000, memory_size=2000000)
+    simd = dict(copy.deepcopy(simd), run_until=20001, warmup=2000, memory_size=20000)
     simd.pop("print_mode", None)
     out["stats_dbr_cfg3_short"] = dict(cfg=simd, resources=resd, products=prodd, policy="dbr", patches=["P2", "P3"],
                                        exp_seed=4242)
@@ -46,7 +46,7 @@ def scenarios_table():
     # breakdowns frequent enough to be seen inside the shortened horizon
     for mode in ("asReady", "onDue"):
         cfg, r20, p20 = sc.jobshop20(run_until=2500, warmup=250, mode=mode)
-        cfg["memory_size"] = 400000
+        cfg["memory_size"] = 20000
         for i, r in enumerate(r20.values()):
             r["tbf"] = {"dist": "expo", "params": [600 + 20 * i]}
         out[f"stats_js20_{mode.lower()}"] = dict(cfg=cfg, resources=r20, products=p20, policy="base",

@@ -132,3 +132,36 @@ def test_sweep_grid_and_flat_slices():
             for s, first, cnt in flat_slices(n_s, reps, world, rank):
                 seen[s, first:first + cnt] += 1
         assert (seen == 1).all()
+
+
+def test_monitor_step_count_matches_the_reference_monitor_process():
+    """print_mode "metrics" (the constructor default) starts the reference's console monitor: it only prints, but its
+    Initialize and Timeout events are Environment.step() calls.  FactorySimulation.monitor_steps() must equal the
+    difference the unmodified reference shows between a run with and without the monitor (factory_sim.py:656-684)."""
+    import contextlib
+    import io
+
+    from manusim_b200.factory_sim import FactorySimulation
+    from oracle import run_reference as rr
+
+    if not rr.reference_available():
+        pytest.skip("/root/reference not mounted")
+    cfg, res, prod = scenarios.toy2(run_until=400, warmup=30)
+    ref = rr.load_reference()
+    for extra in ({}, {"monitor_warmup": 100, "monitor_interval": 100}, {"monitor_interval": 37}, {"monitor_warmup": 400},
+                  {"monitor_warmup": 25, "monitor_interval": 125}):
+        c = dict(cfg, **extra)
+        steps = {}
+        for mode in ("none", "metrics"):
+            sim = ref["FactorySimulation"](dict(c), res, prod, print_mode=mode, seed=5)
+            sim.reset_simulation(5, None)
+            with contextlib.redirect_stdout(io.StringIO()):
+                sim.run_simulation()
+            steps[mode] = next(sim.env._eid) - len(sim.env._queue)
+        ours = FactorySimulation.__new__(FactorySimulation)
+        ours.print_mode, ours.run_until = "metrics", c["run_until"]
+        ours.monitor_warmup = c.get("monitor_warmup", c.get("warmup", 0))
+        ours.monitor_interval = c.get("monitor_interval", int(c["run_until"] / 4))
+        assert ours.monitor_steps() == steps["metrics"] - steps["none"], (extra, steps)
+        ours.print_mode = "none"
+        assert ours.monitor_steps() == 0

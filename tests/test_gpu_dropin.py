@@ -231,6 +231,18 @@ def test_sweep_runner_matches_per_scenario_runs():
     # more demand (smaller gap) => more lost sales or later deliveries, never fewer released orders
     rel = df[(df.variable == "released") & (df.key == "produto01")].set_index("scenario")["mean"]
     assert np.isfinite(rel).all()
+    # a fine grid: many scenarios with few replications each, launched round-robin on 3 streams without a per-scenario
+    # synchronise, tiny pools so that some replications overflow and are re-run at the end -- same moments as scenario by
+    # scenario on one stream
+    grid = {"products.*.demand.freq.params.0": [16.0, 13.0, 11.0, 10.0, 9.0], "products.*.shipping_buffer": [40, 90, 140]}
+    kw = {"dbr_repair": True, "max_production_orders": 40, "max_demand_orders": 12}
+    fine = SweepRunner(DBRSimulation, base, grid, reps=9, seed=5, sim_kwargs=kw, streams=3)
+    fine.run()
+    serial = SweepRunner(DBRSimulation, base, grid, reps=9, seed=5, sim_kwargs=kw, streams=1)
+    serial.run()
+    assert fine.launches == 15 and fine.moments.shape[0] == 15
+    np.testing.assert_allclose(fine.moments, serial.moments, rtol=1e-12, atol=1e-12)
+    assert (fine.moments[:, :, 2].max(axis=1) == 9).all()          # every replication of every scenario is in the statistics
 
 
 def test_host_path_retries_pool_overflow():

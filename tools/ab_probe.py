@@ -29,6 +29,10 @@ sys.path.insert(0, str(ROOT))
 # template parameter + one flush site + cold draws out of line -5 %, calendar pop through the attention word +3 % on top of
 # that, per-stripe earliest onDue timer +2 % -- none beat the plain build, whose 36 KB hot set sits right at the
 # instruction-cache capacity: the response to small code changes is dominated by layout, not by instruction count.
+# third batch (profiles/r02_ab_variants_*.jsonl), each change switchable on its own: delivery mode as a template
+# parameter +7..8 % (job shop) -> adopted for every lean kernel; calendar pop through the attention word + single flush
+# site: -4 % on the FIFO kernels, +9 % max-priority, +6 % DBR -> adopted per kernel family (LOOP2 in msim_kernel.cu);
+# cold draws out of line: +11 % code (the call sequences outweigh the inlined constant test) -> dropped.
 VARIANTS = {
 }
 RESTRICTED = set()

@@ -2,7 +2,7 @@
 
     python tools/summarize_profiles.py launches  gpurun_out/launches_TAG.csv   profiles/TAG_launches.csv
     python tools/summarize_profiles.py full      gpurun_out/prof_TAG.ncu-rep   profiles/TAG_ncu            # one CSV per captured launch
-    python tools/summarize_profiles.py counters  gpurun_out/prof_TAG.ncu-rep   gpurun_out/plain_TAG.log  WORKLOAD
+    python tools/summarize_profiles.py counters  gpurun_out/prof_TAG_part0.ncu-rep,gpurun_out/prof_TAG_part1.ncu-rep  gpurun_out/plain_TAG.log  WORKLOAD
 
 `counters` writes profiles/kernel_counters.json -- the ONLY place bench.py takes ncu-derived numbers from (warp
 instructions per SimPy event, issue-slot utilisation, lanes per instruction, DRAM bytes per algorithmic byte): it joins
@@ -58,11 +58,16 @@ def num(hdr, units, r, name):
     return v * scale
 
 def counters(rep, plain_log, workload):
+    """rep: one report holding one launch per workload part, or a comma-separated list of one-launch reports in part order"""
     line = json.loads([l for l in open(plain_log).read().splitlines() if l.startswith('{')][-1])
     parts = line["roofline"]["kernel_by_part"]
-    hdr, units, data = raw_rows(rep)
+    rows = []                                  # (header, units, row) per captured launch
+    for one in rep.split(","):
+        h, u, d = raw_rows(one)
+        rows += [(h, u, r) for r in d]
+    rep = rep.split(",")[0]
     per_part = []
-    for k, r in enumerate(data):
+    for k, (hdr, units, r) in enumerate(rows):
         if k >= len(parts): break
         p = parts[k]
         ev, alg = p["events_per_launch"], p["algorithmic_bytes_per_launch"]

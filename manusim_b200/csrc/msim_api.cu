@@ -246,7 +246,7 @@ extern "C" int msim_create(const msim_tables_t* t, msim_handle_t* out) {
             size_t need = (size_t)w * L.slab_bytes;
             if (need > smem_blk_max) break;
             int nblk = 0, regs = 0;
-            int rc = sim_kernel_attrs(h->policy, rng, shape, on_due, need, &regs, w * 32, &nblk);
+            int rc = sim_kernel_attrs(h->policy, rng, shape, t->delivery_mode, need, &regs, w * 32, &nblk);
             if (rc != 0) { rc_fit = rc; return f; }
             f.regs = regs;
             if (cta_cap > 0 && nblk > cta_cap) nblk = cta_cap;

@@ -92,7 +92,7 @@ __host__ __device__ constexpr int aos_po_stride(int policy) { return policy == M
 // CTAs, 64 registers -- the default and the only shape of the general kernels; 1: 192 x 6, 56; 2: 256 x 5, 48); the
 // launcher picks the lean kernel itself when the run uses neither queue records nor tape recording.
 int launch_sim(const KParams& p, int policy, int rng_mode, int shape, int grid, int block, size_t smem, void* stream);
-int sim_kernel_attrs(int policy, int rng_mode, int shape, bool on_due, size_t smem, int* regs, int block, int* blocks_per_sm);
+int sim_kernel_attrs(int policy, int rng_mode, int shape, int delivery_mode, size_t smem, int* regs, int block, int* blocks_per_sm);
 int sim_shape_max_warps(int shape);
 int sim_shape_compiled(int shape);       // the shape a request for `shape` is served with in this build
 // launchers implemented in msim_reduce.cu

@@ -195,6 +195,22 @@ __device__ __noinline__ double philox_draw_slow(const KParams& p, Scal* sc, cons
     return out;
 }
 
+// Compile-time tuning per kernel family.  The kernel is instruction-fetch bound and its speed responds to code LAYOUT more
+// than to instruction count: semantically equal variants differ by up to +-14 % on a B200, not monotonically in code size
+// (profiles/r02_ab_variants_*.jsonl; every variant bit-identical on the CPU-fiber emulation first).  What each family
+// gets is what measured best for it:
+//   loop2  calendar pop handed over through the attention word + one flush site   FIFO -4 %, max-priority +9 %, DBR +6 %
+//   emit2  record sequence numbers filled in by the flush, one staging check per dispatched event   } together, with the
+//   mode3  `instantly` delivery compiled as its own kernel instead of a run-time branch in asReady  } rolled Philox rounds:
+//                                                                         max-priority +14 %, FIFO -10 %, DBR 0
+template <int POLICY>
+struct Tune {
+    static constexpr bool prio = POLICY == MSIM_POLICY_MAX_PRIORITY || POLICY == MSIM_POLICY_EDD;
+    static constexpr bool loop2 = POLICY != MSIM_POLICY_FIFO;
+    static constexpr bool emit2 = prio;
+    static constexpr bool mode3 = prio;
+};
+
 // MODE: 0 = the handle delivers asReady or instantly (told apart at run time, a few instructions in INIT_SHIP), 1 = onDue
 // (per-order delivery timers in the calendar), 2 = decided at run time from KParams (the general OPTS = 3 kernels).  The
 // kernel is instruction-fetch bound: compiling the other mode's code out is worth more than the branch it removes.
@@ -226,7 +242,12 @@ struct Sim {
     double& now_d;            // DBR only: exact python-typed clock (now is its float32 view)
     static constexpr bool DBR = POLICY == MSIM_POLICY_DBR;
     static constexpr bool PRIO = POLICY == MSIM_POLICY_MAX_PRIORITY || POLICY == MSIM_POLICY_EDD;
+    static constexpr bool EMIT2 = Tune<POLICY>::emit2;
     __device__ __forceinline__ bool on_due() const { return MODE == 2 ? p.delivery_mode == MSIM_DELIVERY_ON_DUE : MODE == 1; }
+    __device__ __forceinline__ bool instantly() const {
+        if constexpr (Tune<POLICY>::mode3) return MODE == 2 ? p.delivery_mode == MSIM_DELIVERY_INSTANTLY : MODE == 3;
+        else return !on_due() && p.delivery_mode == MSIM_DELIVERY_INSTANTLY;
+    }
 
     __device__ __forceinline__ Sim(const KParams& p_, unsigned char* sb_, Scal* sc_)
         : p(p_), sb(sb_), sc(sc_), uqh(sc_->x_uqh), uqt(sc_->x_uqt), logc(sc_->x_logc), tseq(sc_->x_tseq),
@@ -322,9 +343,16 @@ struct Sim {
 
     // ------------------------------------------------------------------ records (Logger.log, logs.py:44-66)
     __device__ __forceinline__ void emit(int ring, float t, float v) {
-        ARR(uint4, stage)[nstage] = make_uint4(__float_as_uint(t), __float_as_uint(v), (uint32_t)ring, logc + nstage);
-        nstage++;
-        if (nstage >= (uint32_t)kStageFlushAt) attn |= A_FLUSH;
+        if constexpr (EMIT2) {
+            // (the record's sequence number is its position: the flush fills it in; whether the staging area needs flushing
+            //  is looked at once per dispatched event in drain(), not per record -- a dispatch emits at most 7 records)
+            ARR(uint4, stage)[nstage] = make_uint4(__float_as_uint(t), __float_as_uint(v), (uint32_t)ring, 0u);
+            nstage++;
+        } else {
+            ARR(uint4, stage)[nstage] = make_uint4(__float_as_uint(t), __float_as_uint(v), (uint32_t)ring, logc + nstage);
+            nstage++;
+            if (nstage >= (uint32_t)kStageFlushAt) attn |= A_FLUSH;
+        }
     }
     // _log_inventory_metrics, factory_sim.py:551-601 (caller checked warm)
     __device__ __forceinline__ void inventory(int prod, bool with_wip, bool with_fg) {
@@ -859,7 +887,7 @@ struct Sim {
         case OP_INIT_SHIP:                                       // :482-549 (onDue with patch P1)
             // (one finished_goods.get() site for the three delivery modes and the onDue timer: the handler switch is
             //  instruction-cache bound, inlined copies cost more than the branches)
-            if (!on_due() && p.delivery_mode == MSIM_DELIVERY_INSTANTLY) {
+            if (instantly()) {
                 if (!(PRD(float, fg, a) >= DORD(float, qty, b))) {      // lost sale: nothing is taken
                     if (warm) {
                         inventory(a, false, true);
@@ -1053,6 +1081,7 @@ struct Sim {
             }
             dispatch(ev);
             if (nqt - nqh > (uint32_t)p.lay.NQ) fail(MSIM_ST_FIFO_OVERFLOW);
+            if constexpr (EMIT2) { if (nstage >= (uint32_t)kStageFlushAt) return REQ_FLUSH; }
         }
     }
 
@@ -1085,6 +1114,7 @@ struct Sim {
                 nqh++;
             }
             dispatch(ev);       // (single dispatch site: the handler switch must not be inlined twice)
+            if constexpr (EMIT2) { if (nstage >= (uint32_t)kStageFlushAt) return REQ_FLUSH; }
         }
     }
 
@@ -1174,11 +1204,13 @@ __device__ __noinline__ int dbr_cell_order(const KParams& p, const unsigned char
 // replication's HBM ring + fused per-ring reductions.  Lanes holding records of the same ring are grouped with
 // match.any; the group leader adds the group's values in lane (= emission) order, so the float64 sums are
 // deterministic and independent of how replications are sharded.
+template <bool FILLSEQ>
 __device__ __forceinline__ void warp_flush(const KParams& p, const unsigned char* sb, long long rep, int lane, uint32_t n,
                                            uint32_t base) {
     const Lay& L = p.lay;
     uint4 rec = make_uint4(0u, 0u, 0xFFFFFFFFu, 0u);
     if ((uint32_t)lane < n) rec = reinterpret_cast<const uint4*>(sb + L.stage)[lane];
+    if (FILLSEQ) rec.w = base + (uint32_t)lane;
     if ((uint32_t)lane < n && p.a.log != nullptr && rep < p.a.n_log_reps) {
         unsigned long long at = ((unsigned long long)base + (unsigned)lane) % (unsigned long long)p.a.log_cap;
         reinterpret_cast<uint4*>(p.a.log)[rep * p.a.log_cap + (long long)at] = rec;
@@ -1212,7 +1244,7 @@ __global__ void __launch_bounds__(shape_threads(SHAPE), shape_ctas(SHAPE)) sim_k
     Sim<POLICY, RNG, OPTS, MODE> s(p, sb, sc);
     const bool on_due = s.on_due();
     constexpr bool DBR = POLICY == MSIM_POLICY_DBR;
-    constexpr bool LOOP2 = POLICY != MSIM_POLICY_FIFO;      // loop shape per kernel family (see the event loop below)
+    constexpr bool LOOP2 = Tune<POLICY>::loop2;             // loop shape per kernel family (see the event loop below)
     constexpr int kPoStride = aos_po_stride(POLICY), kDoStride = kAosDoLinkStride;
     const uint32_t until_bits = __float_as_uint(p.run_until);
 
@@ -1291,7 +1323,7 @@ __global__ void __launch_bounds__(shape_threads(SHAPE), shape_ctas(SHAPE)) sim_k
                 if (req == REQ_FLUSH) {
                     const uint32_t n = __shfl_sync(FULLMASK, s.nstage, 0);
                     if (n > 0) {
-                        warp_flush(p, sb, rep, lane, n, __shfl_sync(FULLMASK, s.logc, 0));
+                        warp_flush<Tune<POLICY>::emit2>(p, sb, rep, lane, n, __shfl_sync(FULLMASK, s.logc, 0));
                         if (lane == 0) { s.logc += n; s.nstage = 0; }
                         __syncwarp();
                     }
@@ -1304,7 +1336,7 @@ __global__ void __launch_bounds__(shape_threads(SHAPE), shape_ctas(SHAPE)) sim_k
                 req = __shfl_sync(FULLMASK, req, 0);
                 uint32_t n = __shfl_sync(FULLMASK, s.nstage, 0);
                 if (req == REQ_FLUSH) {
-                    warp_flush(p, sb, rep, lane, n, __shfl_sync(FULLMASK, s.logc, 0));
+                    warp_flush<Tune<POLICY>::emit2>(p, sb, rep, lane, n, __shfl_sync(FULLMASK, s.logc, 0));
                     if (lane == 0) { s.logc += n; s.nstage = 0; }
                     __syncwarp();
                     continue;
@@ -1472,7 +1504,7 @@ __global__ void __launch_bounds__(shape_threads(SHAPE), shape_ctas(SHAPE)) sim_k
         if constexpr (!LOOP2) {
             uint32_t n = __shfl_sync(FULLMASK, s.nstage, 0);
             if (n > 0) {
-                warp_flush(p, sb, rep, lane, n, __shfl_sync(FULLMASK, s.logc, 0));
+                warp_flush<Tune<POLICY>::emit2>(p, sb, rep, lane, n, __shfl_sync(FULLMASK, s.logc, 0));
                 if (lane == 0) { s.logc += n; s.nstage = 0; }
                 __syncwarp();
             }
@@ -1510,28 +1542,36 @@ static sim_fn pick_rng(int policy, int rng) {
     return nullptr;
 }
 template <int SHAPE>
-static sim_fn pick_lean(int policy, int rng, bool on_due) {
-    return on_due ? pick_rng<0, SHAPE, 1>(policy, rng) : pick_rng<0, SHAPE, 0>(policy, rng);
+static sim_fn pick_lean(int policy, int rng, int delivery_mode) {
+    if (delivery_mode == MSIM_DELIVERY_INSTANTLY && (policy == MSIM_POLICY_MAX_PRIORITY || policy == MSIM_POLICY_EDD)) {
+        // Tune<POLICY>::mode3 families: `instantly` is its own kernel (MODE 3)
+        if (policy == MSIM_POLICY_MAX_PRIORITY)
+            return rng == MSIM_RNG_REPLAY ? sim_kernel<MSIM_POLICY_MAX_PRIORITY, MSIM_RNG_REPLAY, 0, SHAPE, 3>
+                                          : sim_kernel<MSIM_POLICY_MAX_PRIORITY, MSIM_RNG_PHILOX, 0, SHAPE, 3>;
+        return rng == MSIM_RNG_REPLAY ? sim_kernel<MSIM_POLICY_EDD, MSIM_RNG_REPLAY, 0, SHAPE, 3>
+                                      : sim_kernel<MSIM_POLICY_EDD, MSIM_RNG_PHILOX, 0, SHAPE, 3>;
+    }
+    return delivery_mode == MSIM_DELIVERY_ON_DUE ? pick_rng<0, SHAPE, 1>(policy, rng) : pick_rng<0, SHAPE, 0>(policy, rng);
 }
 // lean: the run uses neither queue records nor tape recording (OPTS = 0) -> one kernel per delivery family; the general
 // kernels (OPTS = 3) decide the delivery mode at run time and exist in the default shape only.  Shapes 0 and 2 are
 // compiled with -DMSIM_ALL_SHAPES=1 (launch-shape sweeps); otherwise every request falls back to shape 1.
-static sim_fn pick(int policy, int rng, bool lean, int shape, bool on_due) {
+static sim_fn pick(int policy, int rng, bool lean, int shape, int delivery_mode) {
     if (!lean) return pick_rng<3, 1, 2>(policy, rng);
 #if MSIM_ALL_SHAPES
-    if (shape == 0) return pick_lean<0>(policy, rng, on_due);
-    if (shape == 2) return pick_lean<2>(policy, rng, on_due);
+    if (shape == 0) return pick_lean<0>(policy, rng, delivery_mode);
+    if (shape == 2) return pick_lean<2>(policy, rng, delivery_mode);
 #endif
-    return pick_lean<1>(policy, rng, on_due);
+    return pick_lean<1>(policy, rng, delivery_mode);
 }
 
 int sim_shape_compiled(int shape) { return MSIM_ALL_SHAPES ? shape : 1; }
 int sim_shape_max_warps(int shape) { return shape_threads(shape) / 32; }
 
-int sim_kernel_attrs(int policy, int rng_mode, int shape, bool on_due, size_t smem, int* regs, int block, int* blocks_per_sm) {
+int sim_kernel_attrs(int policy, int rng_mode, int shape, int delivery_mode, size_t smem, int* regs, int block, int* blocks_per_sm) {
     // residency of the LEAN kernel of this shape; a run that records tapes or logs queue lengths launches the general
     // kernel with the same grid (CTAs that do not fit simply queue)
-    sim_fn f = pick(policy, rng_mode, true, shape, on_due), g = pick(policy, rng_mode, false, shape, on_due);
+    sim_fn f = pick(policy, rng_mode, true, shape, delivery_mode), g = pick(policy, rng_mode, false, shape, delivery_mode);
     if (!f || !g) return MSIM_E_UNSUPPORTED;
     cudaFuncAttributes at;
     if (cudaFuncGetAttributes(&at, f) != cudaSuccess) return MSIM_E_CUDA;
@@ -1552,7 +1592,7 @@ int launch_sim(const KParams& p, int policy, int rng_mode, int shape, int grid, 
     // MSIM_NO_LEAN=1 (diagnostic, tests): always launch the general kernel
     const char* no_lean = getenv("MSIM_NO_LEAN");
     const bool lean = !p.log_queues && p.a.rec_cap == 0 && !(no_lean && no_lean[0] == '1');
-    sim_fn f = pick(policy, rng_mode, lean, shape, p.delivery_mode == MSIM_DELIVERY_ON_DUE);
+    sim_fn f = pick(policy, rng_mode, lean, shape, p.delivery_mode);
     if (!f) return MSIM_E_UNSUPPORTED;
     // The opt-in shared-memory limit is per FUNCTION, not per handle: handles with different slab sizes share a kernel
     // and msim_create lowers the attribute again while it probes CTA widths, so it is set before every launch (a host-

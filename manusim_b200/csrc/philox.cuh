@@ -13,7 +13,13 @@ namespace msim {
 __host__ __device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
                                                        uint32_t k0, uint32_t k1, uint32_t out[4]) {
     const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
+    // the ten rounds stay a loop on the device: the simulation kernel is instruction-fetch bound and every inlined copy of
+    // the unrolled rounds is ~1.3 KB of rarely executed code (profiles/r02_ab_variants_k_*.jsonl)
+#ifdef __CUDA_ARCH__
+#pragma unroll 1
+#else
 #pragma unroll
+#endif
     for (int r = 0; r < 10; ++r) {
         uint64_t p0 = (uint64_t)M0 * c0;
         uint64_t p1 = (uint64_t)M1 * c2;

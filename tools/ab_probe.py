@@ -33,6 +33,9 @@ sys.path.insert(0, str(ROOT))
 # parameter +7..8 % (job shop) -> adopted for every lean kernel; calendar pop through the attention word + single flush
 # site: -4 % on the FIFO kernels, +9 % max-priority, +6 % DBR -> adopted per kernel family (LOOP2 in msim_kernel.cu);
 # cold draws out of line: +11 % code (the call sequences outweigh the inlined constant test) -> dropped.
+# fourth batch (profiles/r02_ab_variants_k_*.jsonl): sequence numbers filled in by the flush + one staging check per dispatch
+# (emit2), `instantly` as its own kernel (mode3), rolled Philox rounds -- together +14 % on the max-priority kernels, -10 % on
+# the FIFO kernels (rolled alone +3 % there) -> per-family compile-time choice (struct Tune in msim_kernel.cu).
 VARIANTS = {
 }
 RESTRICTED = set()

@@ -36,6 +36,9 @@ sys.path.insert(0, str(ROOT))
 # fourth batch (profiles/r02_ab_variants_k_*.jsonl): sequence numbers filled in by the flush + one staging check per dispatch
 # (emit2), `instantly` as its own kernel (mode3), rolled Philox rounds -- together +14 % on the max-priority kernels, -10 % on
 # the FIFO kernels (rolled alone +3 % there) -> per-family compile-time choice (struct Tune in msim_kernel.cu).
+# fifth batch (profiles/r02_ab_variants_n_*.jsonl, tools/experiments/r02_flush2_servefg.patch): log-ring position without the
+# 64-bit modulo + rolled flush loop (-5 % code) and the finished-goods getter service out of line (-1.6 % code): -9 % / -5 %
+# alone, +1 % together on the FIFO kernels -- smaller is not faster on this kernel; left out.
 VARIANTS = {
 }
 RESTRICTED = set()

@@ -70,8 +70,9 @@ def flat_slices(n_scenarios: int, reps: int, world: int, rank: int) -> List[Tupl
 
 class SweepRunner:
     def __init__(self, sim_cls, base: Dict[str, Any], overrides: Dict[str, Sequence[Any]], reps: int, seed: int = 0,
-                 sim_kwargs: Dict[str, Any] | None = None, streams: int = 8):
-        """`streams`: scenario slices are launched round-robin on this many CUDA streams and nobody waits for a single
+                 sim_kwargs: Dict[str, Any] | None = None, streams: int | None = None):
+        """`streams` (default: as many as it takes to keep two waves of resident replications in flight, at most 64):
+        scenario slices are launched round-robin on this many CUDA streams and nobody waits for a single
         scenario: the persistent grids of consecutive scenarios overlap, so a scenario's tail wave (and a fine grid's tiny
         launches) run next to the following scenarios' bodies.  The host synchronises once, after the last launch; pool
         overflows are re-run then (the reduction skips failed replications, a re-run adds its own contribution)."""
@@ -80,7 +81,7 @@ class SweepRunner:
         self.reps = reps
         self.seed = seed
         self.sim_kwargs = sim_kwargs or {}
-        self.streams = max(1, int(streams))
+        self.streams = None if streams is None else max(1, int(streams))
         self.moments = None
         self.events = 0
         self.launches = 0
@@ -104,6 +105,10 @@ class SweepRunner:
         mom = torch.zeros((len(self.points), eng0.K, 3), dtype=torch.float64, device=dev)
         ev_total = torch.zeros((), dtype=torch.int64, device=dev)
         main = torch.cuda.current_stream(dev)
+        if self.streams is None:
+            resident = eng0.info["warps_per_block"] * eng0.info["blocks_per_sm"] * eng0.info["n_sms"]
+            per_slice = max(1, max((c for _, _, c in slices), default=1))
+            self.streams = int(min(64, max(2, -(-2 * resident // per_slice))))
         pool = [torch.cuda.Stream(dev) for _ in range(min(self.streams, max(1, len(slices))))]
         start = torch.cuda.Event()
         start.record(main)

@@ -46,6 +46,9 @@ def main():
         if rank == 0:
             lost = df[(df.variable == "lostSales")].groupby("scenario")["mean"].sum()
             print(json.dumps({"config": 5, "scenarios": len(sw.points), "replications": n_total, "gpus": world, "run_until": ru,
+                              "horizon": ("the shipped toc_dbr horizon" if ru == 200001 else
+                                          f"SHORTENED: run_until={ru} instead of the 200001 of the config-#3 tables"),
+                              "launches": sw.launches, "reruns": sw.reruns, "streams": sw.streams,
                               "wall_s": wall, "events": sw.events, "events_per_s": sw.events / wall,
                               "replications_per_s": n_total / wall,
                               "lost_sales_per_run_min_max": [float(lost.min()), float(lost.max())]}))

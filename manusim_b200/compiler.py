@@ -169,9 +169,14 @@ def _compile_dbr(config, resources, products, t: ScenarioTables, repair: bool) -
     ccr_setup = resources[t.resource_names[ccr]].get("setup", {"params": None}).get("params", [0])[0]
     ccr_pt = np.array([sum([t.step_time[s].raw0 for s in range(t.route_start[p], t.route_start[p + 1])
                             if t.step_resource[s] == ccr]) for p in range(P)], dtype=np.float64)
-    if config.get("sb_update", False) or config.get("cb_update", False):
-        # adjust_shipping_buffer (toc_dbr/simulation.py:357-406) rewrites buffer targets from Python lists at run time
-        raise NotImplementedError("sb_update / cb_update (adaptive DBR buffers) are not supported by the DBR kernel")
+    # sb_update / cb_update (toc_dbr/simulation.py:42-47) are accepted because of what they do in the reference AS SHIPPED:
+    #  * cb_update is read into an attribute and never used;
+    #  * sb_update starts one adjust_shipping_buffer process per product (:357-406), which only adapts a buffer when
+    #    shipping_buffer_penetration[product] holds samples -- and those are appended by process_fg_reduce (:339-355), which
+    #    nothing calls (the base class's hook is _custom_fg_reduced, factory_sim.py:603, and DBRSimulation does not override
+    #    it).  The processes therefore only sleep: same records, same variates, P x (Initialize + Timeouts) more
+    #    Environment.step() calls, which DBRSimulation.host_only_steps() counts.  Checked against the unmodified reference
+    #    in tests/test_dropin_host.py.
     if config.get("min_lotsize", 0):
         # max(replenishment, min_lotsize) turns the lot into a Python int, which changes the dynamic typing of the
         # rope delay (int * float -> float64); not modelled by the DBR kernel yet, so refuse instead of deviating
@@ -181,4 +186,4 @@ def _compile_dbr(config, resources, products, t: ScenarioTables, repair: bool) -
             "interval": interval, "cb_target": float(config.get("cb_target_level", float("inf"))),
             "release_limit": float(config.get("order_release_limit", float("inf"))),
             "ccr_limit": float(config.get("ccr_release_limit", False) or 0.0),
-            "min_lot": float(config.get("min_lotsize", 0))}
+            "min_lot": float(config.get("min_lotsize", 0)), "sb_update": bool(config.get("sb_update", False))}

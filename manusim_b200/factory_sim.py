@@ -99,6 +99,11 @@ class FactorySimulation:
             k += 1
         return 1 + (k + 1)
 
+    def host_only_steps(self) -> int:
+        """Environment.step() calls of reference processes that touch no model state and therefore do not run on the
+        device: the console monitor here, DBRSimulation adds the sleeping adjust_shipping_buffer processes."""
+        return self.monitor_steps()
+
     # ------------------------------------------------------------------ hook policing
     def _check_hooks(self):
         for name in _HOOKS:
@@ -213,7 +218,7 @@ class FactorySimulation:
             raise RuntimeError(f"replication failed: {STATUS_TEXT.get(status, status)}")
         self.env.now = self.run_until
         self.warmup_finished = True
-        self.sim_events = int(res.n_events[0]) + self.monitor_steps()
+        self.sim_events = int(res.n_events[0]) + self.host_only_steps()
         self._acc = (res.acc_sum[0].cpu().numpy(), res.acc_cnt[0].cpu().numpy())
         if n_log:
             count = int(res.log_count[0])
@@ -296,3 +301,24 @@ class DBRSimulation(FactorySimulation):
         self.cb_target_level = d["cb_target"]
         self.contraint_resource = self.tables.resource_names[d["ccr"]]
         self.shipping_buffer = {p: self.products_config[p].get("shipping_buffer", 0) for p in self.products_config.keys()}
+        self.sb_update = bool(self.config.get("sb_update", False))
+        self.cb_update = bool(self.config.get("cb_update", False))       # read and never used by the reference (:43)
+
+    def host_only_steps(self) -> int:
+        """+ the adjust_shipping_buffer processes of sb_update=True (examples/toc_dbr/simulation.py:357-406): as shipped they
+        never see a penetration sample (process_fg_reduce is not wired to the base class's _custom_fg_reduced hook), so each
+        of the P processes is Initialize, Timeout(warmup) and one Timeout(20 * scheduler_interval) after another -- steps
+        only, counted while the instant lies before run_until."""
+        steps = super().host_only_steps()
+        if self.sb_update:
+            per = 1                                                   # Initialize[adjust_shipping_buffer]
+            t, dt = self.warmup, self.scheduler_interval * 20
+            if t < self.run_until:
+                k = int((self.run_until - t) / dt)
+                while t + k * dt >= self.run_until:
+                    k -= 1
+                while t + (k + 1) * dt < self.run_until:
+                    k += 1
+                per += k + 1
+            steps += per * len(self.products_config)
+        return steps

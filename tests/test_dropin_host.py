@@ -165,3 +165,28 @@ def test_monitor_step_count_matches_the_reference_monitor_process():
         assert ours.monitor_steps() == steps["metrics"] - steps["none"], (extra, steps)
         ours.print_mode = "none"
         assert ours.monitor_steps() == 0
+
+
+def test_sb_update_and_cb_update_change_nothing_but_the_step_count_in_the_reference():
+    """examples/toc_dbr sb_update / cb_update as shipped (see manusim_b200/compiler.py): the unmodified reference produces
+    the same records and variates with and without them; sb_update adds the sleeping adjust_shipping_buffer processes'
+    steps, which DBRSimulation.host_only_steps() must reproduce."""
+    from conftest import load_golden
+    from manusim_b200.factory_sim import DBRSimulation
+    from oracle import run_reference as rr
+
+    if not rr.reference_available():
+        pytest.skip("/root/reference not mounted")
+    g = load_golden("dbr_repaired")
+    s = g["scenario"]
+    for horizon in ({}, {"run_until": 2501, "warmup": 1541}):
+        base_cfg = dict(s["cfg"], **horizon)
+        base = rr.run_reference(base_cfg, s["resources"], s["products"], s["seed"], policy="dbr", patches=s["patches"])
+        for extra in ({"sb_update": True}, {"cb_update": True}, {"sb_update": True, "cb_update": True}):
+            cfg = dict(base_cfg, **extra)
+            o = rr.run_reference(cfg, s["resources"], s["products"], s["seed"], policy="dbr", patches=s["patches"])
+            for k in ("ring", "time", "value", "tape_A", "tape_B", "tape_C", "tape_D"):
+                assert np.array_equal(o[k], base[k]), (extra, k)
+            ours = DBRSimulation(cfg, s["resources"], s["products"], print_mode="none", dbr_repair=True)
+            plain = DBRSimulation(base_cfg, s["resources"], s["products"], print_mode="none", dbr_repair=True)
+            assert ours.host_only_steps() - plain.host_only_steps() == o["steps"] - base["steps"], (extra, horizon)

@@ -100,10 +100,12 @@ def test_golden_scenarios_roundtrip_through_compiler():
 
 def test_unsupported_dbr_options_are_refused():
     sim, res, prod, _ = scenarios.load_example("toc_dbr")
-    for key, val in (("min_lotsize", 2), ("sb_update", True), ("cb_update", True)):
-        with pytest.raises(NotImplementedError):
-            compile_scenario(dict(sim, **{key: val}), res, prod, policy="dbr")
+    with pytest.raises(NotImplementedError):
+        compile_scenario(dict(sim, min_lotsize=2), res, prod, policy="dbr")
     compile_scenario(dict(sim, ccr_release_limit=0.6, order_release_limit=3), res, prod, policy="dbr")
+    # sb_update / cb_update: accepted -- as shipped they change no record (see compiler.py), only the step count
+    t = compile_scenario(dict(sim, sb_update=True, cb_update=True), res, prod, policy="dbr")
+    assert t.dbr["sb_update"] is True
 
 
 def test_ctypes_mirror_matches_the_c_header(tmp_path):

@@ -31,6 +31,7 @@ struct msim_handle_s {
     int blocks_per_sm[2];
     int regs[2];
     int shape;                  // launch bounds / register budget of the lean kernels (msim_kernel.cu)
+    bool const_layout;          // the scenario has the standard shape: the lean kernels' constant layout applies
     size_t smem_bytes[2];
     unsigned long long* d_counter;
     double span;                // run_until - warmup
@@ -124,12 +125,11 @@ extern "C" int msim_create(const msim_tables_t* t, msim_handle_t* out) {
     // ---- per-replication slab layout
     int off = 0;
     auto take = [&](int bytes, int align) { off = align_up(off, align); int o = off; off += bytes; return o; };
-    // struct arrays first (resources at slab offset 0, msim_kernel.cu), then what the whole warp reads
-    L.r_utf = take(R * kAosResStride, 4);
-    L.p_fg = take(P * kAosPrdStride, 4);
-    L.po_rel = take(L.MP * aos_po_stride(t->policy), 4);
-    L.do_arr = take(L.MD * kAosDoStride, 4);
-    L.do_prod = take(L.MD * kAosDoLinkStride, 2);
+    // Constant part first, in the order of msim_device.cuh `CL` (resource structs with room for 32, record staging, NORMAL
+    // fifo, URGENT fifo, calendar, (x,u) buffer, scalars, production-order pool): for the standard shape (calendar of 32
+    // slots, NORMAL fifo of 128) these offsets equal the compile-time constants the lean kernels use as immediates; every
+    // kernel can still read them from `Lay`.  Then everything whose place depends on the scenario.
+    L.r_utf = take(CL::kRmax * kAosResStride, 4);
     L.stage = take(kStageCap * 16, 16);
     L.nq = take(L.NQ * 4, 4);
     L.uq = take(L.UQ * 4, 4);
@@ -137,12 +137,16 @@ extern "C" int msim_create(const msim_tables_t* t, msim_handle_t* out) {
     L.tm_eid = take(L.NT * 4, 4);
     L.tm_ev = take(L.NT * 4, 4);
     L.rb = take(2 * 16 * 8, 8);                    // precomputed (x,u) pairs of streams B,C (philox.cuh kXuBuf)
+    L.scal = take((int)sizeof(Scal), 8);
+    L.po_rel = take(L.MP * aos_po_stride(t->policy), 4);
+    L.p_fg = take(P * kAosPrdStride, 4);
+    L.do_arr = take(L.MD * kAosDoStride, 4);
+    L.do_prod = take(L.MD * kAosDoLinkStride, 2);
     L.r_tpy = dbr ? take(R * 8, 8) : 0; L.r_start_d = dbr ? take(R * 8, 8) : 0; L.r_utf_d = dbr ? take(R * 8, 8) : 0;
     L.r_qq = t->log_queues ? take(R * 4, 4) : 0; L.r_lastq = t->log_queues ? take(R * 4, 4) : 0;   // `queue` records only
     L.po_tt = dbr ? take(L.MP * 4, 4) : 0; L.po_eid = dbr ? take(L.MP * 4, 4) : 0;
     L.do_tt = on_due ? take(L.MD * 4, 4) : 0; L.do_eid = on_due ? take(L.MD * 4, 4) : 0;   // delivery timers: onDue only
     L.r_flags = dbr ? take(R, 1) : 0; L.po_relpy = dbr ? take(L.MP, 1) : 0;
-    L.scal = take((int)sizeof(Scal), 8);
     L.slab_bytes = align_up(off, 16);
 
     // ---- scenario table blob (carried in the kernel parameters)
@@ -174,8 +178,13 @@ extern "C" int msim_create(const msim_tables_t* t, msim_handle_t* out) {
             if (t->prod_shipping_buffer) sbuf[p] = t->prod_shipping_buffer[p];
             if (t->dbr_ccr_pt) cpt[p] = t->dbr_ccr_pt[p];
         }
-        L.t_step_dist = put(sd.data(), sd.size() * sizeof(DDist), 8);
+        // constant part first (msim_device.cuh `CL`): setup distributions with room for 32 resources, route starts with
+        // room for 32 products, then the step distributions; the rest follows
+        su.resize(CL::kRmax, to_ddist(msim_dist_t{MSIM_DIST_CONSTANT, 0, 0.0, 0.0, 0.0, 0.0}));
+        rs.resize(CL::kPmax + 1, rs.back());
         L.t_setup = put(su.data(), su.size() * sizeof(DDist), 8);
+        L.t_route_start = put(rs.data(), rs.size() * 2, 2);
+        L.t_step_dist = put(sd.data(), sd.size() * sizeof(DDist), 8);
         L.t_tbf = put(tb.data(), tb.size() * sizeof(DDist), 8);
         L.t_ttr = put(tr.data(), tr.size() * sizeof(DDist), 8);
         L.t_freq = put(fq.data(), fq.size() * sizeof(DDist), 8);
@@ -187,7 +196,6 @@ extern "C" int msim_create(const msim_tables_t* t, msim_handle_t* out) {
         }
         L.t_shipbuf = put(sbuf.data(), sbuf.size() * 8, 8);
         L.t_ccrpt = put(cpt.data(), cpt.size() * 8, 8);
-        L.t_route_start = put(rs.data(), rs.size() * 2, 2);
         L.t_step_res = put(sr.data(), sr.size(), 1);
         blob.resize((blob.size() + 15) / 16 * 16);
         L.t_bytes = (int)blob.size();
@@ -196,6 +204,17 @@ extern "C" int msim_create(const msim_tables_t* t, msim_handle_t* out) {
             return fail(MSIM_E_UNSUPPORTED, "scenario tables exceed the 12 KB kernel-parameter budget (too many route steps)");
         }
         memcpy(h->kp.tblob, blob.data(), blob.size());
+    }
+
+    // do the offsets equal the constants the lean kernels were compiled with?  (the standard shape; anything else runs
+    // the general kernels, which read `Lay`)
+    {
+        const int pol = t->policy;
+        h->const_layout = L.NT == CL::NT && L.NQ == CL::NQ && L.UQ == CL::UQ(pol) && L.stage == CL::stage(pol) &&
+                          L.nq == CL::nq(pol) && L.uq == CL::uq(pol) && L.tm_time == CL::tm_time(pol) &&
+                          L.tm_eid == CL::tm_eid(pol) && L.tm_ev == CL::tm_ev(pol) && L.rb == CL::rb(pol) &&
+                          L.scal == CL::scal(pol) && L.po_rel == CL::po_rel(pol) && L.t_setup == CL::t_setup(pol) &&
+                          L.t_route_start == CL::t_route_start(pol) && L.t_step_dist == CL::t_step_dist(pol);
     }
 
     KParams& kp = h->kp;
@@ -335,7 +354,7 @@ extern "C" int msim_run(msim_handle_t h, const msim_run_args_t* a) {
     long long blocks_needed = (a->n_reps + wpb - 1) / wpb;
     long long grid = (long long)h->n_sms * h->blocks_per_sm[rng];
     if (grid > blocks_needed) grid = blocks_needed;
-    int rc = launch_sim(kp, h->policy, rng, h->shape, (int)grid, wpb * 32, h->smem_bytes[rng], st);
+    int rc = launch_sim(kp, h->policy, rng, h->shape, h->const_layout, (int)grid, wpb * 32, h->smem_bytes[rng], st);
     if (rc != 0) return fail(rc, "simulation kernel launch failed (grid/block/shared-memory configuration)");
     return 0;
 }

@@ -84,6 +84,36 @@ struct KParams {
     msim_run_args_t a;             // device pointers
 };
 
+// Constant part of the layout.  msim_create lays every slab out in this order -- resource structs (room for 32), record
+// staging, NORMAL fifo, URGENT fifo, calendar, (x,u) buffer, scalars, production-order pool, then everything whose place
+// depends on the scenario -- and the scenario tables as setup, route starts, step distributions, then the rest.  When the
+// scenario has the standard shape (calendar of 32 slots: R + P + 2 <= 32; NORMAL fifo of 128; the policy's URGENT fifo) all
+// of these offsets are the compile-time constants below, and the lean kernels (OPTS = 0) use them as immediates instead of
+// loading `Lay` fields from the constant bank and adding them per access (a fifth of a hot handler's instructions).  Other
+// shapes run the general kernels, which always read `Lay`.
+struct CL {
+    static constexpr int kRmax = 32, kPmax = 32;
+    static constexpr int NT = 32, NQ = 128;
+    __host__ __device__ static constexpr int UQ(int policy) { return policy == MSIM_POLICY_DBR ? 64 : 16; }
+    static constexpr int r_utf = 0;
+    static constexpr int stage_ = kRmax * 28;                                            // 896 (16-byte aligned)
+    static constexpr int nq_ = stage_ + kStageCap * 16;                                  // 1408
+    static constexpr int uq_ = nq_ + NQ * 4;                                             // 1920
+    __host__ __device__ static constexpr int stage(int) { return stage_; }
+    __host__ __device__ static constexpr int nq(int) { return nq_; }
+    __host__ __device__ static constexpr int uq(int) { return uq_; }
+    __host__ __device__ static constexpr int tm_time(int policy) { return uq_ + UQ(policy) * 4; }
+    __host__ __device__ static constexpr int tm_eid(int policy) { return tm_time(policy) + NT * 4; }
+    __host__ __device__ static constexpr int tm_ev(int policy) { return tm_eid(policy) + NT * 4; }
+    __host__ __device__ static constexpr int rb(int policy) { return (tm_ev(policy) + NT * 4 + 7) / 8 * 8; }
+    __host__ __device__ static constexpr int scal(int policy) { return (rb(policy) + 2 * 16 * 8 + 7) / 8 * 8; }
+    __host__ __device__ static constexpr int po_rel(int policy) { return (scal(policy) + (int)sizeof(Scal) + 3) / 4 * 4; }
+    // scenario tables
+    __host__ __device__ static constexpr int t_setup(int) { return 0; }
+    __host__ __device__ static constexpr int t_route_start(int) { return kRmax * (int)sizeof(DDist); }
+    __host__ __device__ static constexpr int t_step_dist(int) { return (kRmax * (int)sizeof(DDist) + (kPmax + 1) * 2 + 7) / 8 * 8; }
+};
+
 // struct strides of the entity arrays inside the slab, in bytes (field offsets: msim_kernel.cu)
 constexpr int kAosResStride = 28, kAosPrdStride = 24, kAosDoStride = 12, kAosDoLinkStride = 2;
 __host__ __device__ constexpr int aos_po_stride(int policy) { return policy == MSIM_POLICY_FIFO ? 12 : 16; }   // + prio (PRIO/EDD) or ccr (DBR)
@@ -91,7 +121,8 @@ __host__ __device__ constexpr int aos_po_stride(int policy) { return policy == M
 // launchers implemented in msim_kernel.cu.  `shape` = launch bounds / register budget of the lean kernels (0: 256 x 4
 // CTAs, 64 registers -- the default and the only shape of the general kernels; 1: 192 x 6, 56; 2: 256 x 5, 48); the
 // launcher picks the lean kernel itself when the run uses neither queue records nor tape recording.
-int launch_sim(const KParams& p, int policy, int rng_mode, int shape, int grid, int block, size_t smem, void* stream);
+int launch_sim(const KParams& p, int policy, int rng_mode, int shape, bool const_layout, int grid, int block, size_t smem,
+               void* stream);
 int sim_kernel_attrs(int policy, int rng_mode, int shape, int delivery_mode, size_t smem, int* regs, int block, int* blocks_per_sm);
 int sim_shape_max_warps(int shape);
 int sim_shape_compiled(int shape);       // the shape a request for `shape` is served with in this build

@@ -93,11 +93,17 @@ static_assert(kAosResStride >= 26 && kAosPrdStride >= 24 && kAosDoStride == 12 &
 // table keeps the first field of the SoA slab (p_fg, po_rel, do_arr; do_prod for the demand-order link bytes)
 #define ARR(T, field) (reinterpret_cast<T*>(sb + p.lay.field))
 #define TAB(T, field) (reinterpret_cast<const T*>(p.tblob + p.lay.field))
+// fields of the constant part of the layout (msim_device.cuh `CL`): immediates in the lean kernels (CLAY), `Lay` otherwise
+#define LC(field) (CLAY ? CL::field(POLICY) : p.lay.field)
+#define LCN(field) (CLAY ? CL::field : p.lay.field)               // NT, NQ
+#define LCUQ (CLAY ? CL::UQ(POLICY) : p.lay.UQ)
+#define ARRC(T, field) (reinterpret_cast<T*>(sb + LC(field)))
+#define TABC(T, field) (reinterpret_cast<const T*>(p.tblob + LC(field)))
 #define RES(T, f, i) (*reinterpret_cast<T*>(sb + (uint32_t)(i) * kAosResStride + kRes_##f))
 #define PRD(T, f, i) (*reinterpret_cast<T*>(sb + p.lay.p_fg + (uint32_t)(i) * kAosPrdStride + kPrd_##f))
-#define PORD(T, f, i) (*reinterpret_cast<T*>(sb + p.lay.po_rel + (uint32_t)(i) * kPoStride + kPo_##f))
+#define PORD(T, f, i) (*reinterpret_cast<T*>(sb + LC(po_rel) + (uint32_t)(i) * kPoStride + kPo_##f))
 #define DORD(T, f, i) (*reinterpret_cast<T*>(sb + kDoBase_##f + (uint32_t)(i) * kDoStr_##f + kDo_##f))
-#define PO_NEXT (sb + p.lay.po_rel + kPo_next)
+#define PO_NEXT (sb + LC(po_rel) + kPo_next)
 #define DO_NEXT (sb + p.lay.do_prod + kDo_next)
 
 // Launch syntax and the dynamic shared-memory declaration go through two macros so that the host-side SIMT emulator
@@ -243,6 +249,7 @@ struct Sim {
     static constexpr bool DBR = POLICY == MSIM_POLICY_DBR;
     static constexpr bool PRIO = POLICY == MSIM_POLICY_MAX_PRIORITY || POLICY == MSIM_POLICY_EDD;
     static constexpr bool EMIT2 = Tune<POLICY>::emit2;
+    static constexpr bool CLAY = OPTS == 0;                  // lean kernels: constant layout (msim_device.cuh `CL`)
     __device__ __forceinline__ bool on_due() const { return MODE == 2 ? p.delivery_mode == MSIM_DELIVERY_ON_DUE : MODE == 1; }
     __device__ __forceinline__ bool instantly() const {
         if constexpr (Tune<POLICY>::mode3) return MODE == 2 ? p.delivery_mode == MSIM_DELIVERY_INSTANTLY : MODE == 3;
@@ -264,16 +271,16 @@ struct Sim {
 
     // ------------------------------------------------------------------ event queues
     __device__ __forceinline__ void pushN_raw(uint32_t ev) {
-        ARR(uint32_t, nq)[nqt & (uint32_t)(p.lay.NQ - 1)] = ev;
+        ARRC(uint32_t, nq)[nqt & (uint32_t)(LCN(NQ) - 1)] = ev;
         nqt++;       // overflow is checked once per dispatched event (drain); the ring index is masked, so a
     }                // transient overrun stays inside the slab and aborts the replication with a status code
     __device__ __forceinline__ void pushN(uint32_t ev) { pushN_raw(DBR ? ev | (now_py << 24) : ev); }   // inherits the clock type
     __device__ __forceinline__ void pushU(uint32_t ev) {
         if (DBR) ev |= now_py << 24;
-        ARR(uint32_t, uq)[uqt & (uint32_t)(p.lay.UQ - 1)] = ev;
+        ARRC(uint32_t, uq)[uqt & (uint32_t)(LCUQ - 1)] = ev;
         uqt++;
         attn |= A_URGENT;
-        if (uqt - uqh > (uint32_t)p.lay.UQ) fail(MSIM_ST_FIFO_OVERFLOW);
+        if (uqt - uqh > (uint32_t)LCUQ) fail(MSIM_ST_FIFO_OVERFLOW);
     }
     // env.timeout(delay) issued by a static process that owns calendar slot `slot`
     // `f32`: the delay is float32-typed (false: python int, e.g. the warm-up instant or a zero setup)
@@ -281,9 +288,9 @@ struct Sim {
         if (t == now) {
             if (DBR && f32) pushN_raw(ev); else pushN(ev);   // lands on the current timestamp: larger eid than everything pending
         } else {
-            ARR(float, tm_time)[slot] = t;
-            ARR(uint32_t, tm_eid)[slot] = tseq++;
-            ARR(uint32_t, tm_ev)[slot] = ev;     // what the calendar hands back when this slot fires
+            ARRC(float, tm_time)[slot] = t;
+            ARRC(uint32_t, tm_eid)[slot] = tseq++;
+            ARRC(uint32_t, tm_ev)[slot] = ev;     // what the calendar hands back when this slot fires
         }
     }
 
@@ -296,7 +303,7 @@ struct Sim {
         const uint32_t off = idx - sc->rb_base[stream];
         if (off >= (uint32_t)kXuBuf - kXuRefillAt) rb_need |= 1u << stream;
         if (off >= (uint32_t)kXuBuf || RECORDING) return false;
-        const float2 xu = ARR(float2, rb)[(stream - 1) * kXuBuf + off];
+        const float2 xu = ARRC(float2, rb)[(stream - 1) * kXuBuf + off];
         if (d.kind == MSIM_DIST_NORMAL) {
             v = d.d0 + d.d1 * xu.x;
         } else if ((d.kind == MSIM_DIST_GAMMA || d.kind == MSIM_DIST_ERLANG) && d.d0 >= 1.0f) {
@@ -314,7 +321,7 @@ struct Sim {
         if (RNG == MSIM_RNG_REPLAY) return draw_scalar(stream, d);
         float v;
         if (fast_sample(stream, d, v)) return v > 0.0f ? v : 0.0f;
-        return (float)philox_draw_slow<OPTS>(p, sc, ARR(float2, rb), rep, stream, &d, -1);
+        return (float)philox_draw_slow<OPTS>(p, sc, ARRC(float2, rb), rep, stream, &d, -1);
     }
     // scalar draws of the COLD call sites (demand triplets, breakdowns, boot): one call, no inlined fast path -- the kernel
     // is instruction-fetch bound and these sites run once per order or less (constants are handled inside the callee)
@@ -328,7 +335,7 @@ struct Sim {
             sc->draw[stream]++;
             return d.d0 > 0.0f ? d.d0 : 0.0f;
         }
-        return (float)philox_draw_slow<OPTS>(p, sc, ARR(float2, rb), rep, stream, &d, -1);
+        return (float)philox_draw_slow<OPTS>(p, sc, ARRC(float2, rb), rep, stream, &d, -1);
     }
     __device__ __forceinline__ double draw_batch(const DDist& d, int count) {
         if (RNG == MSIM_RNG_REPLAY) {
@@ -338,7 +345,7 @@ struct Sim {
         }
         float v;
         if (count == 1 && fast_sample(2, d, v)) return (double)((d.kind == MSIM_DIST_NORMAL && !(v > 0.0f)) ? 0.0f : v);
-        return philox_draw_slow<OPTS>(p, sc, ARR(float2, rb), rep, 2, &d, count < 0 ? 0 : count);
+        return philox_draw_slow<OPTS>(p, sc, ARRC(float2, rb), rep, 2, &d, count < 0 ? 0 : count);
     }
 
     // ------------------------------------------------------------------ records (Logger.log, logs.py:44-66)
@@ -346,10 +353,10 @@ struct Sim {
         if constexpr (EMIT2) {
             // (the record's sequence number is its position: the flush fills it in; whether the staging area needs flushing
             //  is looked at once per dispatched event in drain(), not per record -- a dispatch emits at most 7 records)
-            ARR(uint4, stage)[nstage] = make_uint4(__float_as_uint(t), __float_as_uint(v), (uint32_t)ring, 0u);
+            ARRC(uint4, stage)[nstage] = make_uint4(__float_as_uint(t), __float_as_uint(v), (uint32_t)ring, 0u);
             nstage++;
         } else {
-            ARR(uint4, stage)[nstage] = make_uint4(__float_as_uint(t), __float_as_uint(v), (uint32_t)ring, logc + nstage);
+            ARRC(uint4, stage)[nstage] = make_uint4(__float_as_uint(t), __float_as_uint(v), (uint32_t)ring, logc + nstage);
             nstage++;
             if (nstage >= (uint32_t)kStageFlushAt) attn |= A_FLUSH;
         }
@@ -620,7 +627,7 @@ struct Sim {
             break;
         case OP_INIT_RELEASE: {                                  // _release_order :195-211
             int prod = PORD(uint8_t, prod, b);
-            int first = TAB(uint8_t, t_step_res)[TAB(uint16_t, t_route_start)[prod]];
+            int first = TAB(uint8_t, t_step_res)[TABC(uint16_t, t_route_start)[prod]];
             PORD(uint8_t, done, b) = 0;
             PORD(float, rel, b) = now;
             if (DBR) ARR(uint8_t, po_relpy)[b] = (uint8_t)now_py;
@@ -671,7 +678,7 @@ struct Sim {
         }
         // fall through
         case OP_MACH_PUTPROC: {                                  // :397-421 (setup drawn on every operation, quirk E1)
-            float setup = draw_scalar_hot(1, TAB(DDist, t_setup)[a]);
+            float setup = draw_scalar_hot(1, TABC(DDist, t_setup)[a]);
             RES(float, setup, a) = setup;
             if (warm) emit(ringR(RM_SETUP, a), now, setup);
             if (!(force || alone())) PUSH_AND_LEAVE(EV(OP_MACH_REQ, a, 0))
@@ -704,9 +711,9 @@ struct Sim {
         {                                      // :425-440
             uint32_t po = RES(uint8_t, cur, a);
             int prod = PORD(uint8_t, prod, po);
-            int step = TAB(uint16_t, t_route_start)[prod] + PORD(uint8_t, done, po);
+            int step = TABC(uint16_t, t_route_start)[prod] + PORD(uint8_t, done, po);
             RES(float, start, a) = now;
-            double total = draw_batch(TAB(DDist, t_step_dist)[step], (int)PORD(float, qty, po));
+            double total = draw_batch(TABC(DDist, t_step_dist)[step], (int)PORD(float, qty, po));
             if (total < 0.0) { fail(MSIM_ST_NEGATIVE_DELAY); break; }
             if (DBR) {
                 uint8_t fl = ARR(uint8_t, r_flags)[a] & ~(F_TIMER_PY | F_START_PY);
@@ -720,9 +727,9 @@ struct Sim {
                         pushN(EV(OP_TO_PROC, a, 0));
                     } else {
                         ARR(double, r_tpy)[a] = td;
-                        ARR(float, tm_time)[a] = __double2float_rn(td);
-                        ARR(uint32_t, tm_eid)[a] = tseq++;
-                        ARR(uint32_t, tm_ev)[a] = EV(OP_TO_PROC, a, 0);
+                        ARRC(float, tm_time)[a] = __double2float_rn(td);
+                        ARRC(uint32_t, tm_eid)[a] = tseq++;
+                        ARRC(uint32_t, tm_ev)[a] = EV(OP_TO_PROC, a, 0);
                         ARR(uint8_t, r_flags)[a] = fl | F_TIMER_PY;
                     }
                     break;
@@ -813,7 +820,7 @@ struct Sim {
         case OP_TRANS_PUT: {                                     // :306-310 / :329-335
             uint32_t po = RES(uint8_t, tcur, a);
             int prod = PORD(uint8_t, prod, po);
-            int total = TAB(uint16_t, t_route_start)[prod + 1] - TAB(uint16_t, t_route_start)[prod];
+            int total = TABC(uint16_t, t_route_start)[prod + 1] - TABC(uint16_t, t_route_start)[prod];
             PORD(uint8_t, loc, po) = LOC_NONE;
             const bool last = PORD(uint8_t, done, po) == total;
             if (last || !alone()) PUSH_AND_LEAVE(EV(last ? OP_TRANS_GOT2_FINAL : OP_TRANS_GOT2_NEXT, a, 0))
@@ -823,7 +830,7 @@ struct Sim {
         case OP_TRANS_GOT2_NEXT: {                               // :330-336
             uint32_t po = RES(uint8_t, tcur, a);
             int prod = PORD(uint8_t, prod, po);
-            int nxt = TAB(uint8_t, t_step_res)[TAB(uint16_t, t_route_start)[prod] + PORD(uint8_t, done, po)];
+            int nxt = TAB(uint8_t, t_step_res)[TABC(uint16_t, t_route_start)[prod] + PORD(uint8_t, done, po)];
             list_append<kPoStride>(&RES(uint8_t, inh, nxt), &RES(uint8_t, int, nxt), PO_NEXT, po);
             PORD(uint8_t, loc, po) = LOC_IN;
             if (!alone()) PUSH_AND_LEAVE(EV(OP_TRANS_PUTIN, a, nxt))
@@ -961,8 +968,8 @@ struct Sim {
         case OP_DRAIN_GOT:                                       // _update_constraint_buffer :173-190
             if (DBR) {
                 int prod = PORD(uint8_t, prod, b);
-                int step = TAB(uint16_t, t_route_start)[prod] + PORD(uint8_t, done, b) - 1;
-                float mean_pt = __double2float_rn(TAB(DDist, t_step_dist)[step].raw0);
+                int step = TABC(uint16_t, t_route_start)[prod] + PORD(uint8_t, done, b) - 1;
+                float mean_pt = __double2float_rn(TABC(DDist, t_step_dist)[step].raw0);
                 float ccr_time = __fadd_rn(__fmul_rn(mean_pt, PORD(float, qty, b)), __double2float_rn(p.dbr_ccr_setup));
                 sc->cb_level = __fsub_rn(sc->cb_level, ccr_time);
                 if (sc->fin_n) {
@@ -1044,9 +1051,9 @@ struct Sim {
         }
         double nt = __dadd_rn(now_d, p.dbr_interval);            // yield env.timeout(scheduler_interval)
         sc->tick_d = nt;
-        ARR(float, tm_time)[p.lay.R + p.lay.P + 1] = __double2float_rn(nt);
-        ARR(uint32_t, tm_eid)[p.lay.R + p.lay.P + 1] = tseq++;
-        ARR(uint32_t, tm_ev)[p.lay.R + p.lay.P + 1] = EV(OP_TO_TICK, 0, 0);
+        ARRC(float, tm_time)[p.lay.R + p.lay.P + 1] = __double2float_rn(nt);
+        ARRC(uint32_t, tm_eid)[p.lay.R + p.lay.P + 1] = tseq++;
+        ARRC(uint32_t, tm_ev)[p.lay.R + p.lay.P + 1] = EV(OP_TO_TICK, 0, 0);
     }
 
     // lane 0: run zero-delay events until the warp has to cooperate again.  Order of service at one timestamp
@@ -1068,7 +1075,7 @@ struct Sim {
                     ev = pending;
                     attn &= ~A_PENDING;
                 } else if (attn & A_URGENT) {
-                    ev = ARR(uint32_t, uq)[uqh & (uint32_t)(p.lay.UQ - 1)];
+                    ev = ARRC(uint32_t, uq)[uqh & (uint32_t)(LCUQ - 1)];
                     uqh++;
                     if (uqh == uqt) attn &= ~A_URGENT;
                 } else {
@@ -1076,11 +1083,11 @@ struct Sim {
                 }
             } else {
                 if (nqh == nqt) return REQ_ADVANCE;
-                ev = ARR(uint32_t, nq)[nqh & (uint32_t)(p.lay.NQ - 1)];
+                ev = ARRC(uint32_t, nq)[nqh & (uint32_t)(LCN(NQ) - 1)];
                 nqh++;
             }
             dispatch(ev);
-            if (nqt - nqh > (uint32_t)p.lay.NQ) fail(MSIM_ST_FIFO_OVERFLOW);
+            if (nqt - nqh > (uint32_t)LCN(NQ)) fail(MSIM_ST_FIFO_OVERFLOW);
             if constexpr (EMIT2) { if (nstage >= (uint32_t)kStageFlushAt) return REQ_FLUSH; }
         }
     }
@@ -1096,7 +1103,7 @@ struct Sim {
                     ev = pending;
                     attn &= ~A_PENDING;
                 } else if (attn & A_URGENT) {
-                    ev = ARR(uint32_t, uq)[uqh & (uint32_t)(p.lay.UQ - 1)];
+                    ev = ARRC(uint32_t, uq)[uqh & (uint32_t)(LCUQ - 1)];
                     uqh++;
                     if (uqh == uqt) attn &= ~A_URGENT;
                 } else {
@@ -1105,12 +1112,12 @@ struct Sim {
             } else {
                 // one unsigned compare covers both ends: empty fifo (d - 1 wraps) and overrun (d > NQ)
                 const uint32_t d = nqt - nqh;
-                if (d - 1u >= (uint32_t)p.lay.NQ) {
+                if (d - 1u >= (uint32_t)LCN(NQ)) {
                     if (d == 0u) return REQ_ADVANCE;
                     fail(MSIM_ST_FIFO_OVERFLOW);
                     return REQ_DONE;
                 }
-                ev = ARR(uint32_t, nq)[nqh & (uint32_t)(p.lay.NQ - 1)];
+                ev = ARRC(uint32_t, nq)[nqh & (uint32_t)(LCN(NQ) - 1)];
                 nqh++;
             }
             dispatch(ev);       // (single dispatch site: the handler switch must not be inlined twice)
@@ -1205,11 +1212,11 @@ __device__ __noinline__ int dbr_cell_order(const KParams& p, const unsigned char
 // match.any; the group leader adds the group's values in lane (= emission) order, so the float64 sums are
 // deterministic and independent of how replications are sharded.
 template <bool FILLSEQ>
-__device__ __forceinline__ void warp_flush(const KParams& p, const unsigned char* sb, long long rep, int lane, uint32_t n,
-                                           uint32_t base) {
+__device__ __forceinline__ void warp_flush(const KParams& p, const unsigned char* sb, int stage_off, long long rep, int lane,
+                                           uint32_t n, uint32_t base) {
     const Lay& L = p.lay;
     uint4 rec = make_uint4(0u, 0u, 0xFFFFFFFFu, 0u);
-    if ((uint32_t)lane < n) rec = reinterpret_cast<const uint4*>(sb + L.stage)[lane];
+    if ((uint32_t)lane < n) rec = reinterpret_cast<const uint4*>(sb + stage_off)[lane];
     if (FILLSEQ) rec.w = base + (uint32_t)lane;
     if ((uint32_t)lane < n && p.a.log != nullptr && rep < p.a.n_log_reps) {
         unsigned long long at = ((unsigned long long)base + (unsigned)lane) % (unsigned long long)p.a.log_cap;
@@ -1236,11 +1243,12 @@ constexpr int shape_ctas(int shape) { return shape == 1 ? 6 : (shape == 2 ? 5 : 
 template <int POLICY, int RNG, int OPTS, int SHAPE, int MODE>
 __global__ void __launch_bounds__(shape_threads(SHAPE), shape_ctas(SHAPE)) sim_kernel(const __grid_constant__ KParams p) {
     MSIM_DYN_SMEM(smem);
+    constexpr bool CLAY = OPTS == 0;                         // lean kernels: constant layout (msim_device.cuh `CL`)
     const Lay& L = p.lay;
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
     unsigned char* sb = smem + (size_t)warp * L.slab_bytes;
-    Scal* sc = reinterpret_cast<Scal*>(sb + L.scal);
+    Scal* sc = reinterpret_cast<Scal*>(sb + LC(scal));
     Sim<POLICY, RNG, OPTS, MODE> s(p, sb, sc);
     const bool on_due = s.on_due();
     constexpr bool DBR = POLICY == MSIM_POLICY_DBR;
@@ -1260,7 +1268,7 @@ __global__ void __launch_bounds__(shape_threads(SHAPE), shape_ctas(SHAPE)) sim_k
         for (int i = lane; i < L.slab_bytes / 4; i += 32) reinterpret_cast<uint32_t*>(sb)[i] = 0u;
         __syncwarp();
         #pragma unroll 1
-        for (int i = lane; i < L.NT; i += 32) reinterpret_cast<float*>(sb + L.tm_time)[i] = CUDART_INF_F;
+        for (int i = lane; i < LCN(NT); i += 32) reinterpret_cast<float*>(sb + LC(tm_time))[i] = CUDART_INF_F;
         #pragma unroll 1
         for (int i = lane; i < L.MD; i += 32) {
             if (on_due) reinterpret_cast<float*>(sb + L.do_tt)[i] = CUDART_INF_F;
@@ -1323,7 +1331,7 @@ __global__ void __launch_bounds__(shape_threads(SHAPE), shape_ctas(SHAPE)) sim_k
                 if (req == REQ_FLUSH) {
                     const uint32_t n = __shfl_sync(FULLMASK, s.nstage, 0);
                     if (n > 0) {
-                        warp_flush<Tune<POLICY>::emit2>(p, sb, rep, lane, n, __shfl_sync(FULLMASK, s.logc, 0));
+                        warp_flush<Tune<POLICY>::emit2>(p, sb, LC(stage), rep, lane, n, __shfl_sync(FULLMASK, s.logc, 0));
                         if (lane == 0) { s.logc += n; s.nstage = 0; }
                         __syncwarp();
                     }
@@ -1336,7 +1344,7 @@ __global__ void __launch_bounds__(shape_threads(SHAPE), shape_ctas(SHAPE)) sim_k
                 req = __shfl_sync(FULLMASK, req, 0);
                 uint32_t n = __shfl_sync(FULLMASK, s.nstage, 0);
                 if (req == REQ_FLUSH) {
-                    warp_flush<Tune<POLICY>::emit2>(p, sb, rep, lane, n, __shfl_sync(FULLMASK, s.logc, 0));
+                    warp_flush<Tune<POLICY>::emit2>(p, sb, LC(stage), rep, lane, n, __shfl_sync(FULLMASK, s.logc, 0));
                     if (lane == 0) { s.logc += n; s.nstage = 0; }
                     __syncwarp();
                     continue;
@@ -1383,13 +1391,13 @@ __global__ void __launch_bounds__(shape_threads(SHAPE), shape_ctas(SHAPE)) sim_k
             uint32_t bt = 0xFFFFFFFFu, be = 0xFFFFFFFFu;
             int bslot = -1, leq = 0;
             {
-                const uint32_t* tt = reinterpret_cast<const uint32_t*>(sb + L.tm_time);
-                const uint32_t* te = reinterpret_cast<const uint32_t*>(sb + L.tm_eid);
-                if (L.NT == 32) {          // the common shape (R + P + 2 <= 32): one calendar slot per lane
+                const uint32_t* tt = reinterpret_cast<const uint32_t*>(sb + LC(tm_time));
+                const uint32_t* te = reinterpret_cast<const uint32_t*>(sb + LC(tm_eid));
+                if (LCN(NT) == 32) {          // the common shape (R + P + 2 <= 32): one calendar slot per lane
                     bt = tt[lane]; be = te[lane]; bslot = lane; leq = 1;
                 } else {
 #pragma unroll 1
-                    for (int i = lane; i < L.NT; i += 32) {
+                    for (int i = lane; i < LCN(NT); i += 32) {
                         const uint32_t t = tt[i], e = te[i];
                         if (t < bt) { bt = t; be = e; bslot = i; leq = 1; }
                         else if (t == bt) { leq++; if (e < be) { be = e; bslot = i; } }
@@ -1401,8 +1409,8 @@ __global__ void __launch_bounds__(shape_threads(SHAPE), shape_ctas(SHAPE)) sim_k
 #pragma unroll 1
                     for (int i = lane; i < L.MD; i += 32) {
                         const uint32_t t = dt[i], e = de[i];
-                        if (t < bt) { bt = t; be = e; bslot = L.NT + i; leq = 1; }
-                        else if (t == bt) { leq++; if (e < be) { be = e; bslot = L.NT + i; } }
+                        if (t < bt) { bt = t; be = e; bslot = LCN(NT) + i; leq = 1; }
+                        else if (t == bt) { leq++; if (e < be) { be = e; bslot = LCN(NT) + i; } }
                     }
                 }
                 if (DBR) {
@@ -1411,8 +1419,8 @@ __global__ void __launch_bounds__(shape_threads(SHAPE), shape_ctas(SHAPE)) sim_k
 #pragma unroll 1
                     for (int i = lane; i < L.MP; i += 32) {
                         const uint32_t t = pt[i], e = pe[i];
-                        if (t < bt) { bt = t; be = e; bslot = L.NT + L.MD + i; leq = 1; }
-                        else if (t == bt) { leq++; if (e < be) { be = e; bslot = L.NT + L.MD + i; } }
+                        if (t < bt) { bt = t; be = e; bslot = LCN(NT) + L.MD + i; leq = 1; }
+                        else if (t == bt) { leq++; if (e < be) { be = e; bslot = LCN(NT) + L.MD + i; } }
                     }
                 }
             }
@@ -1427,7 +1435,7 @@ __global__ void __launch_bounds__(shape_threads(SHAPE), shape_ctas(SHAPE)) sim_k
                         __syncwarp();
                         if (lane < kXuBuf) {
                             XU r = raw_xu(sc->k0, sc->k1, (uint32_t)st, next + (uint32_t)lane, 0u);
-                            reinterpret_cast<float2*>(sb + L.rb)[(st - 1) * kXuBuf + lane] = make_float2(r.x, r.u);
+                            reinterpret_cast<float2*>(sb + LC(rb))[(st - 1) * kXuBuf + lane] = make_float2(r.x, r.u);
                         }
                         __syncwarp();
                         if (lane == 0) sc->rb_base[st] = next;
@@ -1450,10 +1458,10 @@ __global__ void __launch_bounds__(shape_threads(SHAPE), shape_ctas(SHAPE)) sim_k
             if (DBR && lane == 0 && (cnt > 1u || (s.attn & A_SAME))) {
                 // several calendar entries inside one float32 cell of the clock: python-typed instants order exactly
                 const bool head_py = s.nqh != s.nqt &&
-                    (reinterpret_cast<const uint32_t*>(sb + L.nq)[s.nqh & (uint32_t)(L.NQ - 1)] & EV_PY) != 0u;
+                    (reinterpret_cast<const uint32_t*>(sb + LC(nq))[s.nqh & (uint32_t)(LCN(NQ) - 1)] & EV_PY) != 0u;
                 slot = dbr_cell_order(p, sb, sc, tbits, slot0, s.now_d, head_py);
                 if (slot < 0) {                              // the fifo head belongs to an earlier float64 instant
-                    const uint32_t head_ev = reinterpret_cast<const uint32_t*>(sb + L.nq)[s.nqh & (uint32_t)(L.NQ - 1)];
+                    const uint32_t head_ev = reinterpret_cast<const uint32_t*>(sb + LC(nq))[s.nqh & (uint32_t)(LCN(NQ) - 1)];
                     if constexpr (LOOP2) { s.pending = head_ev; s.attn |= A_PENDING; } else first_ev = head_ev;
                     s.nqh++;
                 }
@@ -1470,9 +1478,9 @@ __global__ void __launch_bounds__(shape_threads(SHAPE), shape_ctas(SHAPE)) sim_k
                 sc->n_timeouts++;
                 uint32_t ev;
                 if (DBR) s.now_py = 0;     // Environment._now takes the type of the popped entry (Appendix B.2)
-                if (slot < L.NT) {
-                    ev = reinterpret_cast<const uint32_t*>(sb + L.tm_ev)[slot];
-                    reinterpret_cast<float*>(sb + L.tm_time)[slot] = CUDART_INF_F;
+                if (slot < LCN(NT)) {
+                    ev = reinterpret_cast<const uint32_t*>(sb + LC(tm_ev))[slot];
+                    reinterpret_cast<float*>(sb + LC(tm_time))[slot] = CUDART_INF_F;
                     if (DBR) {
                         if (slot < L.R) {
                             if ((sb + L.r_flags)[slot] & F_TIMER_PY) {
@@ -1485,12 +1493,12 @@ __global__ void __launch_bounds__(shape_threads(SHAPE), shape_ctas(SHAPE)) sim_k
                             s.now_py = 1; s.now_d = sc->tick_d;
                         }
                     }
-                } else if (on_due && slot < L.NT + L.MD) {
-                    int d = slot - L.NT;
+                } else if (on_due && slot < LCN(NT) + L.MD) {
+                    int d = slot - LCN(NT);
                     ev = EV(OP_TO_SHIP, DORD(uint8_t, prod, d), d);
                     reinterpret_cast<float*>(sb + L.do_tt)[d] = CUDART_INF_F;
                 } else {
-                    int po = slot - L.NT - L.MD;
+                    int po = slot - LCN(NT) - L.MD;
                     ev = EV(OP_TO_DORDER, 0, po);
                     reinterpret_cast<float*>(sb + L.po_tt)[po] = CUDART_INF_F;
                 }
@@ -1504,7 +1512,7 @@ __global__ void __launch_bounds__(shape_threads(SHAPE), shape_ctas(SHAPE)) sim_k
         if constexpr (!LOOP2) {
             uint32_t n = __shfl_sync(FULLMASK, s.nstage, 0);
             if (n > 0) {
-                warp_flush<Tune<POLICY>::emit2>(p, sb, rep, lane, n, __shfl_sync(FULLMASK, s.logc, 0));
+                warp_flush<Tune<POLICY>::emit2>(p, sb, LC(stage), rep, lane, n, __shfl_sync(FULLMASK, s.logc, 0));
                 if (lane == 0) { s.logc += n; s.nstage = 0; }
                 __syncwarp();
             }
@@ -1588,10 +1596,12 @@ int sim_kernel_attrs(int policy, int rng_mode, int shape, int delivery_mode, siz
     return 0;
 }
 
-int launch_sim(const KParams& p, int policy, int rng_mode, int shape, int grid, int block, size_t smem, void* stream) {
-    // MSIM_NO_LEAN=1 (diagnostic, tests): always launch the general kernel
+int launch_sim(const KParams& p, int policy, int rng_mode, int shape, bool const_layout, int grid, int block, size_t smem,
+               void* stream) {
+    // lean kernels: the run uses neither queue records nor tape recording AND the scenario has the standard shape whose
+    // layout offsets they carry as immediates (msim_device.cuh `CL`).  MSIM_NO_LEAN=1 (diagnostic, tests): general kernel.
     const char* no_lean = getenv("MSIM_NO_LEAN");
-    const bool lean = !p.log_queues && p.a.rec_cap == 0 && !(no_lean && no_lean[0] == '1');
+    const bool lean = const_layout && !p.log_queues && p.a.rec_cap == 0 && !(no_lean && no_lean[0] == '1');
     sim_fn f = pick(policy, rng_mode, lean, shape, p.delivery_mode);
     if (!f) return MSIM_E_UNSUPPORTED;
     // The opt-in shared-memory limit is per FUNCTION, not per handle: handles with different slab sizes share a kernel

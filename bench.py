@@ -45,7 +45,7 @@ def workload_spec(name, run_until=None):
         a = scenarios.jobshop20(run_until=ru, warmup=wu, mode="asReady")
         b = scenarios.jobshop20(run_until=ru, warmup=wu, mode="onDue")
         return {"name": name, "parts": [(a, "fifo", 0, 2), (b, "fifo", 1, 2)], "run_until": ru, "warmup": wu,
-                "pools": [(112, 112), (112, 176)],     # (production-order, demand-order) pool sizes; onDue keeps orders until due
+                "pools": [(112, 112), (112, 160)],     # (production-order, demand-order) pool sizes; onDue keeps orders until due
                 "desc": f"jobshop20 (BASELINE config #4: R=20,P=10, setups, TBF/TTR breakdowns, even=asReady/odd=onDue, "
                         f"run_until={ru}, warmup={wu})"}
     if name == "simple_det":

@@ -129,7 +129,7 @@ extern "C" int msim_create(const msim_tables_t* t, msim_handle_t* out) {
     // fifo, URGENT fifo, calendar, (x,u) buffer, scalars, production-order pool): for the standard shape (calendar of 32
     // slots, NORMAL fifo of 128) these offsets equal the compile-time constants the lean kernels use as immediates; every
     // kernel can still read them from `Lay`.  Then everything whose place depends on the scenario.
-    L.r_utf = take(CL::kRmax * kAosResStride, 4);
+    L.r_utf = take((R > CL::kRmax ? R : CL::kRmax) * kAosResStride, 4);
     L.stage = take(kStageCap * 16, 16);
     L.nq = take(L.NQ * 4, 4);
     L.uq = take(L.UQ * 4, 4);
@@ -138,8 +138,8 @@ extern "C" int msim_create(const msim_tables_t* t, msim_handle_t* out) {
     L.tm_ev = take(L.NT * 4, 4);
     L.rb = take(2 * 16 * 8, 8);                    // precomputed (x,u) pairs of streams B,C (philox.cuh kXuBuf)
     L.scal = take((int)sizeof(Scal), 8);
+    L.p_fg = take((P > CL::kPmax ? P : CL::kPmax) * kAosPrdStride, 4);
     L.po_rel = take(L.MP * aos_po_stride(t->policy), 4);
-    L.p_fg = take(P * kAosPrdStride, 4);
     L.do_arr = take(L.MD * kAosDoStride, 4);
     L.do_prod = take(L.MD * kAosDoLinkStride, 2);
     L.r_tpy = dbr ? take(R * 8, 8) : 0; L.r_start_d = dbr ? take(R * 8, 8) : 0; L.r_utf_d = dbr ? take(R * 8, 8) : 0;
@@ -180,10 +180,12 @@ extern "C" int msim_create(const msim_tables_t* t, msim_handle_t* out) {
         }
         // constant part first (msim_device.cuh `CL`): setup distributions with room for 32 resources, route starts with
         // room for 32 products, then the step distributions; the rest follows
-        su.resize(CL::kRmax, to_ddist(msim_dist_t{MSIM_DIST_CONSTANT, 0, 0.0, 0.0, 0.0, 0.0}));
-        rs.resize(CL::kPmax + 1, rs.back());
+        if (R < CL::kRmax) su.resize(CL::kRmax, to_ddist(msim_dist_t{MSIM_DIST_CONSTANT, 0, 0.0, 0.0, 0.0, 0.0}));
+        if (P < CL::kPmax) rs.resize(CL::kPmax + 1, rs.back());
+        if (S < CL::kSmax) sr.resize(CL::kSmax, 0);
         L.t_setup = put(su.data(), su.size() * sizeof(DDist), 8);
         L.t_route_start = put(rs.data(), rs.size() * 2, 2);
+        L.t_step_res = put(sr.data(), sr.size(), 8);
         L.t_step_dist = put(sd.data(), sd.size() * sizeof(DDist), 8);
         L.t_tbf = put(tb.data(), tb.size() * sizeof(DDist), 8);
         L.t_ttr = put(tr.data(), tr.size() * sizeof(DDist), 8);
@@ -196,7 +198,6 @@ extern "C" int msim_create(const msim_tables_t* t, msim_handle_t* out) {
         }
         L.t_shipbuf = put(sbuf.data(), sbuf.size() * 8, 8);
         L.t_ccrpt = put(cpt.data(), cpt.size() * 8, 8);
-        L.t_step_res = put(sr.data(), sr.size(), 1);
         blob.resize((blob.size() + 15) / 16 * 16);
         L.t_bytes = (int)blob.size();
         if (blob.size() > (size_t)kTabMax) {
@@ -213,8 +214,9 @@ extern "C" int msim_create(const msim_tables_t* t, msim_handle_t* out) {
         h->const_layout = L.NT == CL::NT && L.NQ == CL::NQ && L.UQ == CL::UQ(pol) && L.stage == CL::stage(pol) &&
                           L.nq == CL::nq(pol) && L.uq == CL::uq(pol) && L.tm_time == CL::tm_time(pol) &&
                           L.tm_eid == CL::tm_eid(pol) && L.tm_ev == CL::tm_ev(pol) && L.rb == CL::rb(pol) &&
-                          L.scal == CL::scal(pol) && L.po_rel == CL::po_rel(pol) && L.t_setup == CL::t_setup(pol) &&
-                          L.t_route_start == CL::t_route_start(pol) && L.t_step_dist == CL::t_step_dist(pol);
+                          L.scal == CL::scal(pol) && L.p_fg == CL::p_fg(pol) && L.po_rel == CL::po_rel(pol) &&
+                          L.t_setup == CL::t_setup(pol) && L.t_route_start == CL::t_route_start(pol) &&
+                          L.t_step_res == CL::t_step_res(pol) && L.t_step_dist == CL::t_step_dist(pol);
     }
 
     KParams& kp = h->kp;

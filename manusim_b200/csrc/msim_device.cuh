@@ -84,21 +84,22 @@ struct KParams {
     msim_run_args_t a;             // device pointers
 };
 
-// Constant part of the layout.  msim_create lays every slab out in this order -- resource structs (room for 32), record
-// staging, NORMAL fifo, URGENT fifo, calendar, (x,u) buffer, scalars, production-order pool, then everything whose place
-// depends on the scenario -- and the scenario tables as setup, route starts, step distributions, then the rest.  When the
-// scenario has the standard shape (calendar of 32 slots: R + P + 2 <= 32; NORMAL fifo of 128; the policy's URGENT fifo) all
+// Constant part of the layout.  msim_create lays every slab out in this order -- resource structs (room for kRmax), record
+// staging, NORMAL fifo, URGENT fifo, calendar, (x,u) buffer, scalars, product structs (room for kPmax), production-order
+// pool, then everything whose place depends on the scenario -- and the scenario tables as setup, route starts, step
+// resources (room for kSmax), step distributions, then the rest.  When the
+// scenario has the standard shape (R <= 24, P <= 16, <= 256 route steps, NORMAL fifo of 128, the policy's URGENT fifo) all
 // of these offsets are the compile-time constants below, and the lean kernels (OPTS = 0) use them as immediates instead of
 // loading `Lay` fields from the constant bank and adding them per access (a fifth of a hot handler's instructions).  Other
 // shapes run the general kernels, which always read `Lay`.
 struct CL {
-    static constexpr int kRmax = 32, kPmax = 32;
+    static constexpr int kRmax = 24, kPmax = 16, kSmax = 256;     // room reserved for resources / products / route steps
     static constexpr int NT = 32, NQ = 128;
     __host__ __device__ static constexpr int UQ(int policy) { return policy == MSIM_POLICY_DBR ? 64 : 16; }
     static constexpr int r_utf = 0;
-    static constexpr int stage_ = kRmax * 28;                                            // 896 (16-byte aligned)
-    static constexpr int nq_ = stage_ + kStageCap * 16;                                  // 1408
-    static constexpr int uq_ = nq_ + NQ * 4;                                             // 1920
+    static constexpr int stage_ = kRmax * 28;                                            // 672 (16-byte aligned)
+    static constexpr int nq_ = stage_ + kStageCap * 16;                                  // 1184
+    static constexpr int uq_ = nq_ + NQ * 4;                                             // 1696
     __host__ __device__ static constexpr int stage(int) { return stage_; }
     __host__ __device__ static constexpr int nq(int) { return nq_; }
     __host__ __device__ static constexpr int uq(int) { return uq_; }
@@ -107,11 +108,13 @@ struct CL {
     __host__ __device__ static constexpr int tm_ev(int policy) { return tm_eid(policy) + NT * 4; }
     __host__ __device__ static constexpr int rb(int policy) { return (tm_ev(policy) + NT * 4 + 7) / 8 * 8; }
     __host__ __device__ static constexpr int scal(int policy) { return (rb(policy) + 2 * 16 * 8 + 7) / 8 * 8; }
-    __host__ __device__ static constexpr int po_rel(int policy) { return (scal(policy) + (int)sizeof(Scal) + 3) / 4 * 4; }
+    __host__ __device__ static constexpr int p_fg(int policy) { return (scal(policy) + (int)sizeof(Scal) + 3) / 4 * 4; }
+    __host__ __device__ static constexpr int po_rel(int policy) { return p_fg(policy) + kPmax * 24; }
     // scenario tables
     __host__ __device__ static constexpr int t_setup(int) { return 0; }
     __host__ __device__ static constexpr int t_route_start(int) { return kRmax * (int)sizeof(DDist); }
-    __host__ __device__ static constexpr int t_step_dist(int) { return (kRmax * (int)sizeof(DDist) + (kPmax + 1) * 2 + 7) / 8 * 8; }
+    __host__ __device__ static constexpr int t_step_res(int) { return (kRmax * (int)sizeof(DDist) + (kPmax + 1) * 2 + 7) / 8 * 8; }
+    __host__ __device__ static constexpr int t_step_dist(int) { return t_step_res(0) + kSmax; }
 };
 
 // struct strides of the entity arrays inside the slab, in bytes (field offsets: msim_kernel.cu)

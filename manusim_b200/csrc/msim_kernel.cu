@@ -100,7 +100,7 @@ static_assert(kAosResStride >= 26 && kAosPrdStride >= 24 && kAosDoStride == 12 &
 #define ARRC(T, field) (reinterpret_cast<T*>(sb + LC(field)))
 #define TABC(T, field) (reinterpret_cast<const T*>(p.tblob + LC(field)))
 #define RES(T, f, i) (*reinterpret_cast<T*>(sb + (uint32_t)(i) * kAosResStride + kRes_##f))
-#define PRD(T, f, i) (*reinterpret_cast<T*>(sb + p.lay.p_fg + (uint32_t)(i) * kAosPrdStride + kPrd_##f))
+#define PRD(T, f, i) (*reinterpret_cast<T*>(sb + LC(p_fg) + (uint32_t)(i) * kAosPrdStride + kPrd_##f))
 #define PORD(T, f, i) (*reinterpret_cast<T*>(sb + LC(po_rel) + (uint32_t)(i) * kPoStride + kPo_##f))
 #define DORD(T, f, i) (*reinterpret_cast<T*>(sb + kDoBase_##f + (uint32_t)(i) * kDoStr_##f + kDo_##f))
 #define PO_NEXT (sb + LC(po_rel) + kPo_next)
@@ -627,7 +627,7 @@ struct Sim {
             break;
         case OP_INIT_RELEASE: {                                  // _release_order :195-211
             int prod = PORD(uint8_t, prod, b);
-            int first = TAB(uint8_t, t_step_res)[TABC(uint16_t, t_route_start)[prod]];
+            int first = TABC(uint8_t, t_step_res)[TABC(uint16_t, t_route_start)[prod]];
             PORD(uint8_t, done, b) = 0;
             PORD(float, rel, b) = now;
             if (DBR) ARR(uint8_t, po_relpy)[b] = (uint8_t)now_py;
@@ -830,7 +830,7 @@ struct Sim {
         case OP_TRANS_GOT2_NEXT: {                               // :330-336
             uint32_t po = RES(uint8_t, tcur, a);
             int prod = PORD(uint8_t, prod, po);
-            int nxt = TAB(uint8_t, t_step_res)[TABC(uint16_t, t_route_start)[prod] + PORD(uint8_t, done, po)];
+            int nxt = TABC(uint8_t, t_step_res)[TABC(uint16_t, t_route_start)[prod] + PORD(uint8_t, done, po)];
             list_append<kPoStride>(&RES(uint8_t, inh, nxt), &RES(uint8_t, int, nxt), PO_NEXT, po);
             PORD(uint8_t, loc, po) = LOC_IN;
             if (!alone()) PUSH_AND_LEAVE(EV(OP_TRANS_PUTIN, a, nxt))

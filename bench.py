@@ -45,7 +45,8 @@ def workload_spec(name, run_until=None):
         a = scenarios.jobshop20(run_until=ru, warmup=wu, mode="asReady")
         b = scenarios.jobshop20(run_until=ru, warmup=wu, mode="onDue")
         return {"name": name, "parts": [(a, "fifo", 0, 2), (b, "fifo", 1, 2)], "run_until": ru, "warmup": wu,
-                "pools": [(112, 112), (112, 160)],     # (production-order, demand-order) pool sizes; onDue keeps orders until due
+                "pools": [(112, 112), (112, 128)],     # (production-order, demand-order) pool sizes; onDue keeps orders until due
+                                                       # (smaller pools = more resident replications; overflow is re-run)
                 "desc": f"jobshop20 (BASELINE config #4: R=20,P=10, setups, TBF/TTR breakdowns, even=asReady/odd=onDue, "
                         f"run_until={ru}, warmup={wu})"}
     if name == "simple_det":
@@ -230,7 +231,7 @@ def main():
     ap.add_argument("--workload", default="jobshop20")
     ap.add_argument("--reps", type=int, default=0,
                     help="replications per GPU per step (0 = `--waves` full waves of the resident replications)")
-    ap.add_argument("--waves", type=float, default=2.0,
+    ap.add_argument("--waves", type=float, default=4.0,
                     help="with --reps 0: replications per part = waves x (resident warps per SM x SMs) of its kernel, "
                          "the same count for every part (the largest)")
     ap.add_argument("--run-until", type=int, default=None)
@@ -241,10 +242,13 @@ def main():
     ap.add_argument("--fifo", type=int, default=0, help="zero-delay event ring capacity (0 = library default)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true", help="skip the end-to-end leg (profiling runs)")
-    ap.add_argument("--serial-parts", action="store_true", help="launch the workload parts one after the other on one "
-                    "stream (default: one stream per part, so one part's tail wave overlaps the next part's body)")
+    ap.add_argument("--serial-parts", action="store_true", help="(default; kept for old command lines) launch the workload "
+                    "parts one after the other on one stream")
+    ap.add_argument("--concurrent-parts", action="store_true", help="one stream per workload part: two DIFFERENT kernels then "
+                    "share the SMs and their instruction caches, which costs 6-8 %% (profiles/r02_waves_sweep_t.jsonl)")
     ap.add_argument("--no-retry", action="store_true", help="do not re-run pool-overflow replications with big pools")
     args = ap.parse_args()
+    args.serial_parts = not args.concurrent_parts
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3
     if args.impl == "reference":

@@ -57,7 +57,7 @@ def main():
             n_total = a.reps or 1_000_000
             ru = a.run_until or 10000
             parts = []
-            for phase, mode, mdo in ((0, "asReady", 112), (1, "onDue", 176)):
+            for phase, mode, mdo in ((0, "asReady", 112), (1, "onDue", 128)):
                 cfg, res, prod = scenarios.jobshop20(run_until=ru, warmup=ru // 10, mode=mode)
                 parts.append((BatchEngine(compile_scenario(cfg, res, prod, max_production_orders=112, max_demand_orders=mdo)), phase, 2))
         else:

@@ -528,7 +528,7 @@ def main():
             "pool_overflow_replications_rerun": retried[0],
             "status_histogram": fail_codes.tolist(),
             "engine": {k: parts[0]["eng"].info[k] for k in ("smem_per_replication", "warps_per_block", "blocks_per_sm",
-                                                             "regs_per_thread", "n_sms")},
+                                                             "regs_per_thread", "n_sms", "const_layout")},
             "roofline": roofline}
     if rank == 0:
         line["clocks"] = clocks

@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define MSIM_VERSION 200 /* 0.2.0 */
+#define MSIM_VERSION 201 /* 0.2.1 */
 
 /* distribution kinds -- DistributionGenerator.random_number, src/manusim/engine/utils.py:42-67 */
 enum { MSIM_DIST_NONE = -1, MSIM_DIST_CONSTANT = 0, MSIM_DIST_UNIFORM = 1, MSIM_DIST_GAMMA = 2,
@@ -171,6 +171,8 @@ typedef struct msim_info {
     int32_t n_sms;
     int32_t regs_per_thread;
     int32_t max_production_orders, max_demand_orders, fifo_capacity;
+    int32_t const_layout;            /* 1: the slab / tables have the standard constant layout, so runs without queue records
+                                      * and tape recording launch the fast kernels with compile-time offsets; 0: general kernels */
 } msim_info_t;
 
 typedef struct msim_handle_s* msim_handle_t;

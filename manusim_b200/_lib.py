@@ -70,7 +70,7 @@ class Info(C.Structure):
     _fields_ = [("n_rings", C.c_int32), ("smem_per_replication", C.c_int32), ("smem_tables", C.c_int32),
                 ("warps_per_block", C.c_int32), ("blocks_per_sm", C.c_int32), ("n_sms", C.c_int32),
                 ("regs_per_thread", C.c_int32), ("max_production_orders", C.c_int32),
-                ("max_demand_orders", C.c_int32), ("fifo_capacity", C.c_int32)]
+                ("max_demand_orders", C.c_int32), ("fifo_capacity", C.c_int32), ("const_layout", C.c_int32)]
 
 
 _lib = None

@@ -332,6 +332,7 @@ extern "C" int msim_query(msim_handle_t h, msim_info_t* info) {
     info->max_production_orders = L.MP;
     info->max_demand_orders = L.MD;
     info->fifo_capacity = L.NQ;
+    info->const_layout = h->const_layout;
     return 0;
 }
 

@@ -154,3 +154,39 @@ def test_config2_ten_thousand_deterministic_replications_equal_the_oracle_trace(
         ring, tm, val, _ = decode_log(res.log[i].cpu().numpy(), int(res.log_count[i]))
         assert np.array_equal(ring, g["ring"].astype(np.uint32))
         assert np.array_equal(tm, g["time"]) and np.array_equal(val, g["value"])
+
+
+@pytest.mark.parametrize("workload,run_until", [("jobshop20", 2500), ("simple_det", 1000), ("toc_dbr", 4001)])
+def test_benchmarked_fast_kernels_equal_the_oracle_checked_general_kernels(workload, run_until):
+    """The kernels bench.py launches (no queue records, no tape recording, standard shape: compile-time slab / table
+    offsets, `info["const_layout"] == 1`) against the general kernels that the oracle-replay tests above check (tape
+    recording on, run-time offsets): same Philox keys, same pools => identical record streams, step counts and accumulators,
+    record for record.  Closes the chain oracle == general kernel == benchmarked kernel on the bench's own workloads."""
+    import torch
+
+    import bench
+    from manusim_b200 import BatchEngine, compile_scenario
+
+    spec = bench.workload_spec(workload, run_until)
+    for i, ((cfg, res, prod), policy, _, _) in enumerate(spec["parts"]):
+        mpo, mdo = spec.get("pools", [(0, 0)] * len(spec["parts"]))[i]
+        eng = BatchEngine(compile_scenario(cfg, res, prod, policy=policy, dbr_repair=spec.get("dbr_repair", False),
+                                           max_production_orders=mpo, max_demand_orders=mdo))
+        assert eng.info["const_layout"] == 1, "the bench workloads must run on the fast path"
+        n, cap = 64, 1 << 17
+        fast = eng.run(n, seed=4242 + i, n_log_reps=n, log_cap=cap)
+        general = eng.run(n, seed=4242 + i, n_log_reps=n, log_cap=cap, record_tapes=1 << 16)
+        torch.cuda.synchronize()
+        st = fast.status.cpu().numpy()
+        assert np.array_equal(st, general.status.cpu().numpy())
+        ok = st == 0                      # a pool overflow stops both kernels at the same event
+        assert ok.sum() >= n - 4, st
+        assert np.array_equal(fast.n_events.cpu().numpy(), general.n_events.cpu().numpy())
+        lc = fast.log_count.cpu().numpy()
+        assert np.array_equal(lc, general.log_count.cpu().numpy()) and lc.max() <= cap
+        fl, gl = fast.log.cpu().numpy(), general.log.cpu().numpy()
+        for r in np.nonzero(ok)[0]:
+            assert np.array_equal(fl[r, : lc[r]], gl[r, : lc[r]]), (workload, i, int(r))
+        assert np.array_equal(fast.acc_cnt.cpu().numpy()[ok], general.acc_cnt.cpu().numpy()[ok])
+        assert np.array_equal(fast.acc_sum.cpu().numpy()[ok].view(np.uint64), general.acc_sum.cpu().numpy()[ok].view(np.uint64))
+        eng.close()

@@ -67,7 +67,7 @@ def test_library_exports_every_declared_symbol():
     lib = _lib.load()
     for name in declared:
         assert hasattr(lib, name)
-    assert lib.msim_version() == 200
+    assert lib.msim_version() == 201
     # struct sizes of the ctypes mirror match the header's layout (all 8-byte aligned fields)
     assert ctypes.sizeof(_lib.Dist) == 40
     assert ctypes.sizeof(_lib.RunArgs) % 8 == 0 and ctypes.sizeof(_lib.Tables) % 8 == 0

@@ -53,6 +53,12 @@ def expand_grid(base: Dict[str, Any], overrides: Dict[str, Sequence[Any]]) -> Li
     return out
 
 
+def kernel_family(sim) -> Tuple[int, int, int, int]:
+    """Which simulation kernel a scenario launches: policy, delivery family, queue records, constant layout."""
+    t = sim.tables
+    return (int(t.policy), int(t.delivery_mode), int(bool(t.log_queues)), int(sim.engine.info.get("const_layout", 0)))
+
+
 def flat_slices(n_scenarios: int, reps: int, world: int, rank: int) -> List[Tuple[int, int, int]]:
     """[(scenario, first replication, count)] owned by `rank` when the flattened (scenario, replication) space is
     split contiguously over `world` ranks."""
@@ -86,6 +92,7 @@ class SweepRunner:
         self.events = 0
         self.launches = 0
         self.reruns = 0
+        self.kernel_families = 1
 
     def _new_sim(self, s):
         _, tree = self.points[s]
@@ -116,8 +123,26 @@ class SweepRunner:
             st.wait_event(start)
         pending = []                                   # (sim, result, scenario, first, count): kept alive until the sync
         sims = {slices[0][0]: first_sim} if slices else {}
+        for s, _, _ in slices:
+            if s not in sims:
+                sims[s] = self._new_sim(s)
+        # Slices that run the SAME kernel share the SMs on concurrent streams; slices of DIFFERENT kernels (a sweep over
+        # delivery_mode, or shapes on and off the constant layout) must not: two instruction streams per SM cost an
+        # instruction-fetch-bound kernel 6-8 % (profiles/r02_waves_sweep_t.jsonl).  Launch kernel family by kernel family.
+        slices = sorted(slices, key=lambda sl: (kernel_family(sims[sl[0]]), sl[0], sl[1]))
+        family = None
         for i, (s, first, cnt) in enumerate(slices):
-            sim = sims.get(s) or sims.setdefault(s, self._new_sim(s))
+            sim = sims[s]
+            if kernel_family(sim) != family:
+                if family is not None:
+                    fence = [torch.cuda.Event() for _ in pool]
+                    for ev, q in zip(fence, pool):
+                        ev.record(q)
+                    for q in pool:
+                        for ev in fence:
+                            q.wait_event(ev)
+                    self.kernel_families += 1
+                family = kernel_family(sim)
             st = pool[i % len(pool)]
             # replication key = f(seed of the scenario, replication index within the scenario): shard-invariant
             with torch.cuda.stream(st):

@@ -245,6 +245,31 @@ def test_sweep_runner_matches_per_scenario_runs():
     assert (fine.moments[:, :, 2].max(axis=1) == 9).all()          # every replication of every scenario is in the statistics
 
 
+def test_sweep_over_delivery_modes_launches_kernel_family_by_kernel_family():
+    """A sweep whose scenarios need DIFFERENT kernels (delivery families) groups its launches by kernel and fences the
+    streams between the groups; statistics equal the scenario-by-scenario runs."""
+    import torch
+
+    from manusim_b200 import scenarios
+    from manusim_b200.factory_sim import FactorySimulation
+    from manusim_b200.sweep import SweepRunner
+
+    cfg, res, prod = scenarios.jobshop20(run_until=400, warmup=50, mode="asReady")
+    base = {"simulation": cfg, "resources": res, "products": prod}
+    grid = {"simulation.delivery_mode": ["asReady", "onDue"], "products.*.demand.freq.params.0": [10.0, 12.0, 14.0]}
+    sw = SweepRunner(FactorySimulation, base, grid, reps=40, seed=3, streams=3)
+    sw.run()
+    assert sw.kernel_families == 2 and sw.launches == 6
+    for s in (1, 4):
+        _, tree = sw.points[s]
+        one = FactorySimulation(tree["simulation"], tree["resources"], tree["products"], print_mode="none")
+        m = one.engine.reduce(one.engine.run(40, seed=3 + 1000003 * s))
+        torch.cuda.synchronize()
+        np.testing.assert_allclose(sw.moments[s], m.cpu().numpy(), rtol=1e-12)
+    modes = [sw.points[s][1]["simulation"]["delivery_mode"] for s in range(6)]
+    assert sorted(set(modes)) == ["asReady", "onDue"]
+
+
 def test_host_path_retries_pool_overflow():
     import torch
 

@@ -20,6 +20,7 @@ from __future__ import annotations
 
 import argparse
 import json
+import math
 import os
 import subprocess
 import sys
@@ -281,8 +282,14 @@ def main():
     if args.reps > 0:
         reps = args.reps
     else:
-        # every part simulates the same number of replications (the workload alternates them by index parity)
-        reps = int(round(args.waves * max(p["resident"] for p in parts))) * max(p["period"] for p in parts)
+        # every part simulates the same number of replications (the workload alternates them by index parity): at least
+        # `waves` waves of the part with the most resident replications, rounded up to WHOLE waves of every part when the
+        # parts' kernels hold different numbers of replications (a last wave that fills 40 % of the SMs costs a whole one)
+        per_part = int(round(args.waves * max(p["resident"] for p in parts)))
+        whole = math.lcm(*[p["resident"] for p in parts])
+        if -(-per_part // whole) * whole <= 2 * per_part:
+            per_part = -(-per_part // whole) * whole
+        reps = per_part * max(p["period"] for p in parts)
     for p in parts:
         p["n"] = reps // p["period"]
     K = parts[0]["eng"].K

@@ -277,7 +277,7 @@ def main():
         eng = BatchEngine(compile_scenario(cfg, res, prod, policy=policy, dbr_repair=spec.get("dbr_repair", False),
                                            max_production_orders=args.max_po or mpo,
                                            max_demand_orders=args.max_do or mdo, fifo_capacity=args.fifo))
-        resident = eng.info["warps_per_block"] * eng.info["blocks_per_sm"] * eng.info["n_sms"]
+        resident = eng.resident_replications
         parts.append({"eng": eng, "phase": phase, "period": period, "resident": resident})
     if args.reps > 0:
         reps = args.reps

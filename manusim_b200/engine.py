@@ -122,6 +122,12 @@ class BatchEngine:
         self.info = {f[0]: getattr(info, f[0]) for f in _lib.Info._fields_}
         self.K = info.n_rings
 
+    @property
+    def resident_replications(self) -> int:
+        """Replications the GPU simulates at once (one per resident warp).  Kernel time is quantised in waves of this many:
+        a batch that is a multiple of it wastes nothing, a half-filled last wave costs 0.7 of a whole one."""
+        return int(self.info["warps_per_block"] * self.info["blocks_per_sm"] * self.info["n_sms"])
+
     def synchronize(self):
         self.torch.cuda.synchronize(self.device)
 

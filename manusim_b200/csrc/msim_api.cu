@@ -276,11 +276,11 @@ extern "C" int msim_create(const msim_tables_t* t, msim_handle_t* out) {
         return f;
     };
     int shape = shape_forced >= 0 ? shape_forced : 1;
-    if (shape_forced < 0 && sim_shape_compiled(0) == 0) {
+    if (shape_forced < 0 && sim_shape_compiled(0, t->delivery_mode) == 0) {
         Fit f1 = fit(1, MSIM_RNG_PHILOX), f0 = fit(0, MSIM_RNG_PHILOX);
         if (rc_fit == 0 && f0.total >= f1.total) shape = 0;      // no residency to gain from the smaller register budget
     }
-    shape = sim_shape_compiled(shape);
+    shape = sim_shape_compiled(shape, t->delivery_mode);
     h->shape = shape;
     for (int rng = 0; rng < 2 && rc_fit == 0; ++rng) {
         Fit f = fit(shape, rng);

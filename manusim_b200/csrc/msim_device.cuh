@@ -128,7 +128,7 @@ int launch_sim(const KParams& p, int policy, int rng_mode, int shape, bool const
                void* stream);
 int sim_kernel_attrs(int policy, int rng_mode, int shape, int delivery_mode, size_t smem, int* regs, int block, int* blocks_per_sm);
 int sim_shape_max_warps(int shape);
-int sim_shape_compiled(int shape);       // the shape a request for `shape` is served with in this build
+int sim_shape_compiled(int shape, int delivery_mode);   // the shape a request for `shape` is served with in this build
 // launchers implemented in msim_reduce.cu
 int launch_reduce(const double* acc_sum, const uint32_t* acc_cnt, const int32_t* status, int64_t n_reps, int K, int P,
                   int R, double span, double* out, void* stream);

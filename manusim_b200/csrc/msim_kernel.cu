@@ -1563,17 +1563,24 @@ static sim_fn pick_lean(int policy, int rng, int delivery_mode) {
 }
 // lean: the run uses neither queue records nor tape recording (OPTS = 0) -> one kernel per delivery family; the general
 // kernels (OPTS = 3) decide the delivery mode at run time and exist in the default shape only.  Shapes 0 and 2 are
-// compiled with -DMSIM_ALL_SHAPES=1 (launch-shape sweeps); otherwise every request falls back to shape 1.
+// compiled with -DMSIM_ALL_SHAPES=1 (launch-shape sweeps); otherwise every request falls back to shape 1 -- except the
+// onDue family, which also exists in shape 0: its per-order delivery timers make the slab so large that shared memory holds
+// 30-32 warps per SM whatever the register budget, so it takes the 64 registers (+3..7 %, profiles/r02_ab_ondue_64regs_z.jsonl).
 static sim_fn pick(int policy, int rng, bool lean, int shape, int delivery_mode) {
     if (!lean) return pick_rng<3, 1, 2>(policy, rng);
 #if MSIM_ALL_SHAPES
     if (shape == 0) return pick_lean<0>(policy, rng, delivery_mode);
     if (shape == 2) return pick_lean<2>(policy, rng, delivery_mode);
+#else
+    if (shape == 0 && delivery_mode == MSIM_DELIVERY_ON_DUE) return pick_rng<0, 0, 1>(policy, rng);
 #endif
     return pick_lean<1>(policy, rng, delivery_mode);
 }
 
-int sim_shape_compiled(int shape) { return MSIM_ALL_SHAPES ? shape : 1; }
+int sim_shape_compiled(int shape, int delivery_mode) {
+    if (MSIM_ALL_SHAPES) return shape;
+    return shape == 0 && delivery_mode == MSIM_DELIVERY_ON_DUE ? 0 : 1;
+}
 int sim_shape_max_warps(int shape) { return shape_threads(shape) / 32; }
 
 int sim_kernel_attrs(int policy, int rng_mode, int shape, int delivery_mode, size_t smem, int* regs, int block, int* blocks_per_sm) {
@@ -1604,6 +1611,14 @@ int launch_sim(const KParams& p, int policy, int rng_mode, int shape, bool const
     const bool lean = const_layout && !p.log_queues && p.a.rec_cap == 0 && !(no_lean && no_lean[0] == '1');
     sim_fn f = pick(policy, rng_mode, lean, shape, p.delivery_mode);
     if (!f) return MSIM_E_UNSUPPORTED;
+    if (!lean && block > shape_threads(1)) {
+        // the general kernels exist in the 192-thread shape only: same slabs, narrower CTAs, proportionally more of them
+        // (a persistent grid pulling replications from a counter: CTAs that do not fit simply queue)
+        const int wpb = block / 32, w1 = shape_threads(1) / 32;
+        grid = (int)(((long long)grid * wpb + w1 - 1) / w1);
+        smem = smem / (size_t)wpb * (size_t)w1;
+        block = w1 * 32;
+    }
     // The opt-in shared-memory limit is per FUNCTION, not per handle: handles with different slab sizes share a kernel
     // and msim_create lowers the attribute again while it probes CTA widths, so it is set before every launch (a host-
     // side attribute write, negligible next to the launch).

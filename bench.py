@@ -72,6 +72,16 @@ def workload_spec(name, run_until=None):
     raise SystemExit(f"unknown workload {name}")
 
 
+def whole_wave_batch(residents, waves):
+    """Replications per workload part: `waves` waves of the part with the most resident replications, rounded up to whole
+    waves of EVERY part (kernel time is quantised in waves: a half-filled last wave costs 0.7 of a whole one,
+    profiles/r02_wave_quantisation_x.jsonl) unless that would more than double the batch."""
+    per_part = int(round(waves * max(residents)))
+    whole = math.lcm(*[int(r) for r in residents])
+    rounded = -(-per_part // whole) * whole
+    return rounded if rounded <= 2 * per_part else per_part
+
+
 def rep_keys(seed, idx):
     from manusim_b200.engine import rep_keys as _rk
 
@@ -285,11 +295,7 @@ def main():
         # every part simulates the same number of replications (the workload alternates them by index parity): at least
         # `waves` waves of the part with the most resident replications, rounded up to WHOLE waves of every part when the
         # parts' kernels hold different numbers of replications (a last wave that fills 40 % of the SMs costs a whole one)
-        per_part = int(round(args.waves * max(p["resident"] for p in parts)))
-        whole = math.lcm(*[p["resident"] for p in parts])
-        if -(-per_part // whole) * whole <= 2 * per_part:
-            per_part = -(-per_part // whole) * whole
-        reps = per_part * max(p["period"] for p in parts)
+        reps = whole_wave_batch([p["resident"] for p in parts], args.waves) * max(p["period"] for p in parts)
     for p in parts:
         p["n"] = reps // p["period"]
     K = parts[0]["eng"].K

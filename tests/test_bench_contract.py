@@ -84,3 +84,15 @@ def test_bench_workloads_compile_on_cpu():
             assert t.n_rings == 11 * t.P + 4 * t.R + 3
     keys = bench.rep_keys(20260101, __import__("numpy").arange(4))
     assert len(set(keys.tolist())) == 4
+
+
+def test_batch_is_sized_in_whole_waves_of_every_part():
+    """bench.py sizes a step as whole waves of every workload part's kernel (wave quantisation)."""
+    import bench
+
+    sm = 148
+    assert bench.whole_wave_batch([36 * sm, 32 * sm], 4.0) == 8 * 36 * sm == 9 * 32 * sm      # config #4 on a B200
+    assert bench.whole_wave_batch([36 * sm, 30 * sm], 4.0) == 5 * 36 * sm == 6 * 30 * sm
+    assert bench.whole_wave_batch([36 * sm], 4.0) == 4 * 36 * sm                             # one part: nothing to round
+    assert bench.whole_wave_batch([36 * sm, 36 * sm], 2.0) == 2 * 36 * sm
+    assert bench.whole_wave_batch([36 * sm, 31 * sm], 1.0) == 36 * sm                        # common multiple too far: keep

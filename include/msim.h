@@ -185,7 +185,8 @@ int msim_create(const msim_tables_t* tables, msim_handle_t* out);
 int msim_destroy(msim_handle_t h);
 int msim_query(msim_handle_t h, msim_info_t* info);
 
-/* run n_reps replications; device buffers; asynchronous on args->stream */
+/* run n_reps replications; device buffers; asynchronous on args->stream.  A handle may be launched on several streams at
+ * once (every launch takes its own work counter; up to 64 launches of one handle in flight). */
 int msim_run(msim_handle_t h, const msim_run_args_t* args);
 /* same, host buffers, synchronous (H2D + kernel + D2H inside the call) */
 int msim_run_host(msim_handle_t h, const msim_host_args_t* args);

@@ -9,6 +9,7 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <atomic>
 #include <string>
 #include <vector>
 #include "msim_device.cuh"
@@ -33,12 +34,15 @@ struct msim_handle_s {
     int shape;                  // launch bounds / register budget of the lean kernels (msim_kernel.cu)
     bool const_layout;          // the scenario has the standard shape: the lean kernels' constant layout applies
     size_t smem_bytes[2];
-    unsigned long long* d_counter;
+    unsigned long long* d_counter;      // kCounters work counters: every launch takes the next one, so launches of one
+    std::atomic<unsigned> run_seq{0};   // handle on different streams never share a counter
     double span;                // run_until - warmup
     // scratch for msim_run_host
     void* d_scratch; size_t scratch_bytes;
     cudaEvent_t ev0, ev1;
 };
+
+constexpr unsigned kCounters = 64;
 
 static int align_up(int x, int a) { return (x + a - 1) / a * a; }
 
@@ -295,7 +299,7 @@ extern "C" int msim_create(const msim_tables_t* t, msim_handle_t* out) {
         delete h;
         return fail(rc_fit, rc_fit == MSIM_E_UNSUPPORTED ? "policy not available in this build" : "kernel attribute query failed");
     }
-    if (cudaMalloc(&h->d_counter, 8) != cudaSuccess) {
+    if (cudaMalloc(&h->d_counter, 8 * kCounters) != cudaSuccess) {
         delete h;
         return fail(MSIM_E_NOMEM, "cudaMalloc failed");
     }
@@ -350,7 +354,8 @@ extern "C" int msim_run(msim_handle_t h, const msim_run_args_t* a) {
     kp.a = *a;
     if (!a->log) { kp.a.n_log_reps = 0; }
     cudaStream_t st = (cudaStream_t)a->stream;
-    CU(cudaMemsetAsync(h->d_counter, 0, 8, st));
+    kp.work_counter = h->d_counter + h->run_seq.fetch_add(1u) % kCounters;
+    CU(cudaMemsetAsync(kp.work_counter, 0, 8, st));
     const int rng = a->rng_mode;
     const int wpb = h->warps_per_block[rng];
     kp.warps_per_block = wpb;

@@ -16,7 +16,7 @@ def main():
     ap.add_argument("--config", type=int, default=4)
     ap.add_argument("--reps", type=int, default=0)
     ap.add_argument("--run-until", type=int, default=0)
-    ap.add_argument("--chunk", type=int, default=65536)
+    ap.add_argument("--chunk", type=int, default=0, help="replications per round of launches; 0 = whole waves of every part's kernel, about 3e5")
     a = ap.parse_args()
     import torch, torch.distributed as dist
     from manusim_b200 import BatchEngine, compile_scenario, scenarios
@@ -74,8 +74,14 @@ def main():
         ev = torch.zeros((), dtype=torch.int64, device=dev)
         fails = torch.zeros((), dtype=torch.int64, device=dev)
         rerun = 0
-        for c0 in range(lo, hi, a.chunk):
-            c1 = min(hi, c0 + a.chunk)
+        chunk = a.chunk
+        if chunk <= 0:
+            # kernel time is quantised in waves of resident replications: size a round as whole waves of every part
+            import math
+            whole = math.lcm(*[eng.resident_replications for eng, _, _ in parts]) * max(per for _, _, per in parts)
+            chunk = whole * max(1, 300_000 // whole)
+        for c0 in range(lo, hi, chunk):
+            c1 = min(hi, c0 + chunk)
             for eng, phase, period in parts:
                 g = np.arange(c0, c1, dtype=np.int64)
                 g = g[g % period == phase]

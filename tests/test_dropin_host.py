@@ -134,6 +134,29 @@ def test_sweep_grid_and_flat_slices():
         assert (seen == 1).all()
 
 
+def test_sweep_kernel_family_groups_scenarios_by_the_kernel_they_launch():
+    """SweepRunner launches kernel family by kernel family: scenarios that differ only in numbers share a family, a
+    different delivery mode, policy, queue-record switch or an off-standard shape does not."""
+    from types import SimpleNamespace as NS
+
+    from manusim_b200 import compile_scenario
+    from manusim_b200.sweep import kernel_family
+
+    def fam(cfg, res, prod, const_layout=1, **kw):
+        return kernel_family(NS(tables=compile_scenario(cfg, res, prod, **kw), engine=NS(info={"const_layout": const_layout})))
+
+    cfg, res, prod = scenarios.jobshop20(run_until=300, warmup=30, mode="asReady")
+    a = fam(cfg, res, prod)
+    slower = {k: dict(v, demand=dict(v["demand"], freq={"dist": "expo", "params": [14.0]})) for k, v in prod.items()}
+    assert fam(cfg, res, slower) == a
+    assert fam(dict(cfg, delivery_mode="onDue"), res, prod) != a
+    assert fam(cfg, res, prod, policy="max_priority") != a
+    assert fam(dict(cfg, log_queues=True), res, prod) != a
+    assert fam(cfg, res, prod, const_layout=0) != a
+    order = sorted([fam(dict(cfg, delivery_mode=m), res, prod) for m in ("onDue", "asReady", "onDue", "asReady")])
+    assert order[0] == order[1] and order[2] == order[3] and order[1] != order[2]
+
+
 def test_monitor_step_count_matches_the_reference_monitor_process():
     """print_mode "metrics" (the constructor default) starts the reference's console monitor: it only prints, but its
     Initialize and Timeout events are Environment.step() calls.  FactorySimulation.monitor_steps() must equal the

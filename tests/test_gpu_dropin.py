@@ -376,3 +376,26 @@ def test_device_variable_moments_equal_host_computation(tmp_path):
     st = pd.read_csv(tmp_path / "experiment_stats_device_variables.csv")
     assert list(st["variable"])[:3] == ["deliveredOntime", "deliveredLate", "lostSales"] and len(st) == 18
     assert st["size"].between(0, 5).all() and (st["size"] == 5).sum() >= 10
+
+
+def test_one_engine_on_two_streams_at_once():
+    """Every launch takes its own work counter: two launches of ONE handle in flight on different streams give the
+    replications each of them was asked for (msim.h, msim_run)."""
+    import torch
+
+    from manusim_b200 import BatchEngine, compile_scenario, scenarios
+
+    cfg, res, prod = scenarios.jobshop20(run_until=600, warmup=60, mode="asReady")
+    eng = BatchEngine(compile_scenario(cfg, res, prod))
+    n = 3 * eng.resident_replications // 2
+    ref_a, ref_b = eng.run(n, seed=5), eng.run(n, seed=6)
+    torch.cuda.synchronize()
+    sa, sb = torch.cuda.Stream(), torch.cuda.Stream()
+    a = eng.run(n, seed=5, stream=sa)
+    b = eng.run(n, seed=6, stream=sb)
+    torch.cuda.synchronize()
+    for x, y in ((a, ref_a), (b, ref_b)):
+        assert (x.status == 0).all()
+        assert torch.equal(x.n_events, y.n_events) and torch.equal(x.acc_cnt, y.acc_cnt)
+        assert torch.equal(x.acc_sum.view(torch.int64), y.acc_sum.view(torch.int64))
+    eng.close()

@@ -22,7 +22,7 @@ sys.path.insert(0, str(ROOT / "tests"))
 
 
 def main() -> int:
-    from conftest import ERROR_NAMES, GOLDEN_NAMES, ORACLE_POLICY, load_golden
+    from conftest import ERROR_NAMES, GOLDEN_NAMES, ORACLE_ONLY_NAMES, ORACLE_POLICY, load_golden
 
     from oracle import factory_oracle as fo
     from oracle import run_reference as rr
@@ -31,7 +31,7 @@ def main() -> int:
         print(json.dumps({"error": "the real simpy package was not selected (set ORACLE_SIMPY=real)"}))
         return 2
     bad = 0
-    for name in GOLDEN_NAMES + ERROR_NAMES:
+    for name in GOLDEN_NAMES + ORACLE_ONLY_NAMES + ERROR_NAMES:
         g = load_golden(name)
         s = g["scenario"]
         row = {"scenario": name, "engine": fo.SIMPY_ENGINE}

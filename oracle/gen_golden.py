@@ -140,6 +140,13 @@ def scenario_table():
     # with this seed it diverges at t = 4322.37 -- 39 844 differing records and another step count up to t = 8001)
     out["dbr_f64_order"] = dict(cfg=dict(sim_t, run_until=5001, warmup=4000), resources=res_t, products=prod,
                                 policy="dbr", seed=8, patches=["P2", "P3"])
+    # ORACLE-ONLY goldens (tests/conftest.py ORACLE_ONLY_NAMES): min_lotsize != 0 (toc_dbr/simulation.py:222-229) turns the
+    # lot into a python int / float, the CCR time into a float64 product and the rope delay into a python-typed Timeout.
+    # The kernel refuses the option; the traveling oracle is pinned on it all the same.
+    out["dbr_min_lot"] = dict(cfg=dict(sim, run_until=3001, warmup=300, min_lotsize=2), resources=res, products=prod,
+                              policy="dbr", seed=1234, patches=["P2", "P3"])
+    out["dbr_min_lot_frac"] = dict(cfg=dict(sim, run_until=2001, warmup=300, min_lotsize=2.5), resources=res,
+                                   products=prod, policy="dbr", seed=99, patches=["P2", "P3"])
     # zero setups and zero-time operations under max-priority dispatch: the machine finishes whole operations inside one
     # timestamp while the transport chain of the previous order is still being processed (event order within a
     # timestamp; the kernel's "machine chain ahead of the transport chain" shortcut needed OP_HOP for this)

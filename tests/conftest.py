@@ -34,3 +34,5 @@ GOLDEN_NAMES = ["toy2", "toy2_instantly", "ss_cfg1", "ss_det", "ss_instantly", "
                 "js20_ondue", "js20_breakdowns", "dbr_shipped", "dbr_repaired", "dbr_typed", "ss_queues", "dbr_limits",
                 "ss_ondue", "js20_lots_queues", "dbr_ondue", "dbr_tiny_setup", "ss_zero_ops", "dbr_mixed_types", "dbr_f64_order"]
 ERROR_NAMES = ["err_negdelay", "err_amount"]
+# pinned for the oracle only: options the kernel refuses (compile_scenario raises NotImplementedError)
+ORACLE_ONLY_NAMES = ["dbr_min_lot", "dbr_min_lot_frac"]

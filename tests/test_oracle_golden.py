@@ -3,7 +3,7 @@ against golden vectors produced by executing the UNMODIFIED reference (oracle/ge
 import numpy as np
 import pytest
 
-from conftest import ERROR_NAMES, GOLDEN_NAMES, ORACLE_POLICY, load_golden
+from conftest import ERROR_NAMES, GOLDEN_NAMES, ORACLE_ONLY_NAMES, ORACLE_POLICY, load_golden
 from oracle.factory_oracle import metrics_from_trace, run_oracle
 
 FAST = [n for n in GOLDEN_NAMES if n not in ("js20_ondue", "js20_breakdowns")]
@@ -15,7 +15,7 @@ def _run(g, tapes=None):
                       ORACLE_POLICY[s["policy"]], tapes=tapes, dbr_repair="P3" in s["patches"])
 
 
-@pytest.mark.parametrize("name", GOLDEN_NAMES)
+@pytest.mark.parametrize("name", GOLDEN_NAMES + ORACLE_ONLY_NAMES)
 def test_oracle_matches_reference_seeded(name):
     g = load_golden(name)
     o = _run(g)
@@ -26,7 +26,7 @@ def test_oracle_matches_reference_seeded(name):
         assert np.array_equal(o[k].view(np.uint8), g[k].view(np.uint8)), k
 
 
-@pytest.mark.parametrize("name", FAST)
+@pytest.mark.parametrize("name", FAST + ORACLE_ONLY_NAMES)
 def test_oracle_matches_reference_in_replay(name):
     g = load_golden(name)
     o = _run(g, tapes={k: g["tape_" + k] for k in "ABCD"})

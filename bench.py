@@ -75,11 +75,12 @@ def workload_spec(name, run_until=None):
 def whole_wave_batch(residents, waves):
     """Replications per workload part: `waves` waves of the part with the most resident replications, rounded up to whole
     waves of EVERY part (kernel time is quantised in waves: a half-filled last wave costs 0.7 of a whole one,
-    profiles/r02_wave_quantisation_x.jsonl) unless that would more than double the batch."""
+    profiles/r02_wave_quantisation_x.jsonl) unless that would grow the batch -- and with it the duration of a step -- by
+    more than a quarter."""
     per_part = int(round(waves * max(residents)))
     whole = math.lcm(*[int(r) for r in residents])
     rounded = -(-per_part // whole) * whole
-    return rounded if rounded <= 2 * per_part else per_part
+    return rounded if 4 * rounded <= 5 * per_part else per_part
 
 
 def rep_keys(seed, idx):

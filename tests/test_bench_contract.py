@@ -91,7 +91,8 @@ def test_batch_is_sized_in_whole_waves_of_every_part():
     import bench
 
     sm = 148
-    assert bench.whole_wave_batch([36 * sm, 32 * sm], 4.0) == 8 * 36 * sm == 9 * 32 * sm      # config #4 on a B200
+    assert bench.whole_wave_batch([36 * sm, 32 * sm], 8.0) == 8 * 36 * sm == 9 * 32 * sm      # config #4 on a B200
+    assert bench.whole_wave_batch([36 * sm, 32 * sm], 4.0) == 4 * 36 * sm                     # 8 / 9 waves would double a step
     assert bench.whole_wave_batch([36 * sm, 30 * sm], 4.0) == 5 * 36 * sm == 6 * 30 * sm
     assert bench.whole_wave_batch([36 * sm], 4.0) == 4 * 36 * sm                             # one part: nothing to round
     assert bench.whole_wave_batch([36 * sm, 36 * sm], 2.0) == 2 * 36 * sm

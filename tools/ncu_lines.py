@@ -35,14 +35,21 @@ ex, sz, st, per_line = collections.Counter(), collections.Counter(), collections
 for s, (kk, f, hi) in enumerate(kern):
     if kk != a.kernel: continue
     hdr = rows[hi]; ie = hdr.index("Instructions Executed"); isamp = hdr.index("# Samples")
+    cur = None                                         # the source line the following SASS rows belong to
     for r in rows[hi + 1: hdr_idx[s + 1] - 2]:
-        if len(r) <= ie or not r[0].isdigit(): continue
+        if len(r) <= ie: continue
+        if not r[0].isdigit():
+            # a SASS row ("", "", address, instruction, ...) under its source line: 16 bytes of code
+            if cur is not None and len(r) > 2 and r[2].strip().startswith("0x"):
+                sz[cur[0]] += 16
+                if cur[1] in per_line: per_line[cur[1]][1] += 16
+            continue
         ln = int(r[0]); v = int(r[ie] or 0); smp = int(r[isamp] or 0)
         key = region(ln) if "msim_kernel" in f else f
+        cur = (key, ln if "msim_kernel" in f else None)
         ex[key] += v; st[key] += smp
-        if len(r) > 2 and r[2].strip().startswith("0x"): sz[key] += 16
         if "msim_kernel" in f:
-            e = per_line.setdefault(ln, [0, 0, 0, r[1]]); e[0] += v; e[1] += 16 if (len(r) > 2 and r[2].strip().startswith("0x")) else 0; e[2] += smp
+            e = per_line.setdefault(ln, [0, 0, 0, r[1]]); e[0] += v; e[2] += smp
 T, S, Z = sum(ex.values()), sum(st.values()), sum(sz.values())
 print(f"kernel {a.kernel}: {T / a.events:.1f} warp instr/event, {Z / 1024:.1f} KB SASS, {S} stall samples")
 print(" instr/ev   KB   stall%  region")
